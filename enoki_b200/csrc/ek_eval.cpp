@@ -1,0 +1,1137 @@
+/*
+ * ek_eval.cpp -- scheduler + sweep-program assembler + launcher (cuda_eval).
+ *
+ * Behavioural spec: src/cuda/jit.cu:1385-1508 (sweep_recursive / cuda_eval) and
+ * :983-1227 (cuda_jit_assemble) of the reference:
+ *   - live roots are grouped by array size, scheduled DFS post-order with the
+ *     heavier subtree first, one kernel per group;
+ *   - a variable is STORED by a kernel iff it is externally referenced, has no
+ *     side effect and has the sweep's size (jit.cu:1027-1030,1165-1169);
+ *   - after evaluation the dependencies of stored variables are dropped
+ *     (jit.cu:1484-1507).
+ * New here:
+ *   - the group program is a list of EkInstr (ek_isa.h) for ek_sweep_kernel
+ *     instead of PTX text; a linear-scan allocator maps values to shared-memory
+ *     slots, forwarding single-use values through registers;
+ *   - "phases": horizontal reductions are lazy size-1 variables computed as an
+ *     epilogue of the sweep that produces their operand; consumers of a reduction
+ *     (and wide consumers of a computed size-1 value) are scheduled in a later
+ *     phase, so `x / hsum(x)` needs no host round trip.
+ */
+#include "ek_internal.h"
+static_assert(sizeof(EkSweepArgs) <= 4096, "EkSweepArgs must fit the classic kernel parameter space");
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <functional>
+#include <sstream>
+#include <unordered_set>
+
+namespace {
+
+inline bool is_reduce(ek_op op) { return op >= EK_OP_HSUM && op <= EK_OP_COUNT; }
+
+struct Loc {
+    enum Kind : uint8_t { NONE, UNI, STAGED, SLOT, PENDING } kind = NONE;
+    uint16_t idx = 0;       /* uniform word / staged unit / slot */
+};
+
+struct Group {
+    uint32_t phase = 0;
+    size_t size = 0;
+    std::vector<uint32_t> roots;
+    std::vector<uint32_t> sched;
+    std::unordered_set<uint32_t> visited;
+};
+
+struct Output { uint32_t var; uint32_t argw; size_t bytes; };
+
+struct Assembled {
+    std::vector<EkInstr> init, body, fini;
+    std::vector<uint32_t> lits;
+    std::vector<uint32_t> argw;                 /* pointer words are patched at launch */
+    struct PtrFix { uint32_t argw; uint32_t var; bool output; };
+    std::vector<PtrFix> ptr_fix;                /* argw index <- data pointer of var */
+    std::vector<Output> outputs;                /* variables that receive storage    */
+    struct Staged { uint32_t var; uint16_t unit; uint8_t esize; };
+    std::vector<Staged> staged;
+    struct Scalar { uint32_t var; };
+    std::vector<Scalar> scalars;
+    uint32_t n_tmp = 0, n_in_units = 0, n_red = 0;
+    uint32_t extra_bytes = 0;
+    uint32_t n_arith = 0;
+    uint64_t bytes_in = 0, bytes_out = 0;
+    struct DescFix { uint32_t argw; uint32_t count_limit; };
+    std::vector<uint32_t> copies_fix;           /* argw index of Desc.copies (set from config) */
+    std::string error;
+};
+
+struct Config { int V; uint32_t T; uint32_t stages; uint32_t ctas_per_sm; size_t smem; uint32_t off_bar, off_prog, off_extra, off_slots; bool prog_in_smem; };
+
+/* ------------------------------------------------------------------ device opcode selection */
+enum Cls { C_F32, C_F64, C_I32, C_U32, C_I64, C_U64, C_BAD };
+
+Cls cls_of(ek_type t) {
+    switch (t) {
+        case EK_FLOAT32: return C_F32;
+        case EK_FLOAT64: return C_F64;
+        case EK_INT8: case EK_INT16: case EK_INT32: return C_I32;
+        case EK_UINT8: case EK_UINT16: case EK_UINT32: case EK_BOOL: return C_U32;
+        case EK_INT64: return C_I64;
+        case EK_UINT64: case EK_POINTER: return C_U64;
+        default: return C_BAD;
+    }
+}
+
+/* normalisation op that brings a 32-bit register back into the value range of a narrow type */
+int norm_op(ek_type t) {
+    switch (t) {
+        case EK_INT8: return DOP_SEXT8;
+        case EK_UINT8: return DOP_ZEXT8;
+        case EK_INT16: return DOP_SEXT16;
+        case EK_UINT16: return DOP_ZEXT16;
+        default: return -1;
+    }
+}
+
+#define SEL(f32, f64, i32, u32, i64, u64) \
+    (c == C_F32 ? (f32) : c == C_F64 ? (f64) : c == C_I32 ? (i32) : c == C_U32 ? (u32) : c == C_I64 ? (i64) : (u64))
+
+/* returns device opcode or -1 */
+int pick_op(ek_op op, ek_type vt, ek_type at /* operand type */) {
+    Cls c = cls_of(op >= EK_OP_GT && op <= EK_OP_NE ? at : vt);
+    if (c == C_BAD) return -1;
+    switch (op) {
+        case EK_OP_MOV:   return SEL(DOP_MOV_32, DOP_MOV_64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
+        case EK_OP_NEG:   return SEL(DOP_NEG_F32, DOP_NEG_F64, DOP_NEG_I32, DOP_NEG_I32, DOP_NEG_I64, DOP_NEG_I64);
+        case EK_OP_ABS:   return SEL(DOP_ABS_F32, DOP_ABS_F64, DOP_ABS_I32, DOP_MOV_32, DOP_ABS_I64, DOP_MOV_64);
+        case EK_OP_SQRT:  return SEL(DOP_SQRT_F32, DOP_SQRT_F64, -1, -1, -1, -1);
+        case EK_OP_RCP:   return SEL(DOP_RCP_F32, DOP_RCP_F64, -1, -1, -1, -1);
+        case EK_OP_RSQRT: return SEL(DOP_RSQRT_F32, DOP_RSQRT_F64, -1, -1, -1, -1);
+        case EK_OP_EXP:   return SEL(DOP_EXP_F32, DOP_EXP_F64, -1, -1, -1, -1);
+        case EK_OP_LOG:   return SEL(DOP_LOG_F32, DOP_LOG_F64, -1, -1, -1, -1);
+        case EK_OP_SIN:   return SEL(DOP_SIN_F32, DOP_SIN_F64, -1, -1, -1, -1);
+        case EK_OP_COS:   return SEL(DOP_COS_F32, DOP_COS_F64, -1, -1, -1, -1);
+        case EK_OP_FLOOR: return SEL(DOP_FLOOR_F32, DOP_FLOOR_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
+        case EK_OP_CEIL:  return SEL(DOP_CEIL_F32, DOP_CEIL_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
+        case EK_OP_ROUND: return SEL(DOP_ROUND_F32, DOP_ROUND_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
+        case EK_OP_TRUNC: return SEL(DOP_TRUNC_F32, DOP_TRUNC_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
+        case EK_OP_NOT:   return vt == EK_BOOL ? DOP_NOT_B : SEL(DOP_NOT_32, DOP_NOT_64, DOP_NOT_32, DOP_NOT_32, DOP_NOT_64, DOP_NOT_64);
+        case EK_OP_POPC:  return SEL(-1, -1, DOP_POPC_32, DOP_POPC_32, DOP_POPC_64, DOP_POPC_64);
+        case EK_OP_CLZ:   return SEL(-1, -1, DOP_CLZ_32, DOP_CLZ_32, DOP_CLZ_64, DOP_CLZ_64);
+        case EK_OP_CTZ:   return SEL(-1, -1, DOP_CTZ_32, DOP_CTZ_32, DOP_CTZ_64, DOP_CTZ_64);
+        case EK_OP_ADD:   return SEL(DOP_ADD_F32, DOP_ADD_F64, DOP_ADD_I32, DOP_ADD_I32, DOP_ADD_I64, DOP_ADD_I64);
+        case EK_OP_SUB:   return SEL(DOP_SUB_F32, DOP_SUB_F64, DOP_SUB_I32, DOP_SUB_I32, DOP_SUB_I64, DOP_SUB_I64);
+        case EK_OP_MUL:   return SEL(DOP_MUL_F32, DOP_MUL_F64, DOP_MUL_I32, DOP_MUL_I32, DOP_MUL_I64, DOP_MUL_I64);
+        case EK_OP_MULHI: return SEL(-1, -1, DOP_MULHI_I32, DOP_MULHI_U32, DOP_MULHI_I64, DOP_MULHI_U64);
+        case EK_OP_DIV:   return SEL(DOP_DIV_F32, DOP_DIV_F64, DOP_DIV_I32, DOP_DIV_U32, DOP_DIV_I64, DOP_DIV_U64);
+        case EK_OP_MOD:   return SEL(-1, -1, DOP_MOD_I32, DOP_MOD_U32, DOP_MOD_I64, DOP_MOD_U64);
+        case EK_OP_MIN:   return SEL(DOP_MIN_F32, DOP_MIN_F64, DOP_MIN_I32, DOP_MIN_U32, DOP_MIN_I64, DOP_MIN_U64);
+        case EK_OP_MAX:   return SEL(DOP_MAX_F32, DOP_MAX_F64, DOP_MAX_I32, DOP_MAX_U32, DOP_MAX_I64, DOP_MAX_U64);
+        case EK_OP_SHL:   return SEL(-1, -1, DOP_SHL_32, DOP_SHL_32, DOP_SHL_64, DOP_SHL_64);
+        case EK_OP_SHR:   return SEL(-1, -1, DOP_SHR_I32, DOP_SHR_U32, DOP_SHR_I64, DOP_SHR_U64);
+        case EK_OP_AND:   return SEL(DOP_AND_32, DOP_AND_64, DOP_AND_32, DOP_AND_32, DOP_AND_64, DOP_AND_64);
+        case EK_OP_OR:    return SEL(DOP_OR_32, DOP_OR_64, DOP_OR_32, DOP_OR_32, DOP_OR_64, DOP_OR_64);
+        case EK_OP_XOR:   return SEL(DOP_XOR_32, DOP_XOR_64, DOP_XOR_32, DOP_XOR_32, DOP_XOR_64, DOP_XOR_64);
+        case EK_OP_GT:    return SEL(DOP_GT_F32, DOP_GT_F64, DOP_GT_I32, DOP_GT_U32, DOP_GT_I64, DOP_GT_U64);
+        case EK_OP_GE:    return SEL(DOP_GE_F32, DOP_GE_F64, DOP_GE_I32, DOP_GE_U32, DOP_GE_I64, DOP_GE_U64);
+        case EK_OP_LT:    return SEL(DOP_LT_F32, DOP_LT_F64, DOP_LT_I32, DOP_LT_U32, DOP_LT_I64, DOP_LT_U64);
+        case EK_OP_LE:    return SEL(DOP_LE_F32, DOP_LE_F64, DOP_LE_I32, DOP_LE_U32, DOP_LE_I64, DOP_LE_U64);
+        case EK_OP_EQ:    return SEL(DOP_EQ_F32, DOP_EQ_F64, DOP_EQ_32, DOP_EQ_32, DOP_EQ_64, DOP_EQ_64);
+        case EK_OP_NE:    return SEL(DOP_NE_F32, DOP_NE_F64, DOP_NE_32, DOP_NE_32, DOP_NE_64, DOP_NE_64);
+        case EK_OP_MUL_NZ: return SEL(DOP_MULNZ_F32, DOP_MULNZ_F64, -1, -1, -1, -1);
+        case EK_OP_FMA:   return SEL(DOP_FMA_F32, DOP_FMA_F64, DOP_MAD_I32, DOP_MAD_I32, DOP_MAD_I64, DOP_MAD_I64);
+        case EK_OP_FMA_NZ: return SEL(DOP_FMANZ_F32, DOP_FMANZ_F64, -1, -1, -1, -1);
+        case EK_OP_SELECT: return SEL(DOP_SELECT_32, DOP_SELECT_64, DOP_SELECT_32, DOP_SELECT_32, DOP_SELECT_64, DOP_SELECT_64);
+        default: return -1;
+    }
+}
+
+/* conversion src -> dst (cuda.h:236-247); mode = rounding for float->int */
+int pick_cvt(ek_type src, ek_type dst) {
+    Cls s = cls_of(src), d = cls_of(dst);
+    if (s == C_BAD || d == C_BAD) return -1;
+    static const int tab[6][6] = {
+        /* from F32 */ { DOP_MOV_32, DOP_CVT_F32_F64, DOP_CVT_F32_I32, DOP_CVT_F32_U32, DOP_CVT_F32_I64, DOP_CVT_F32_U64 },
+        /* from F64 */ { DOP_CVT_F64_F32, DOP_MOV_64, DOP_CVT_F64_I32, DOP_CVT_F64_U32, DOP_CVT_F64_I64, DOP_CVT_F64_U64 },
+        /* from I32 */ { DOP_CVT_I32_F32, DOP_CVT_I32_F64, DOP_MOV_32, DOP_MOV_32, DOP_CVT_I32_I64, DOP_CVT_I32_I64 },
+        /* from U32 */ { DOP_CVT_U32_F32, DOP_CVT_U32_F64, DOP_MOV_32, DOP_MOV_32, DOP_CVT_U32_U64, DOP_CVT_U32_U64 },
+        /* from I64 */ { DOP_CVT_I64_F32, DOP_CVT_I64_F64, DOP_CVT_64_32, DOP_CVT_64_32, DOP_MOV_64, DOP_MOV_64 },
+        /* from U64 */ { DOP_CVT_U64_F32, DOP_CVT_U64_F64, DOP_CVT_64_32, DOP_CVT_64_32, DOP_MOV_64, DOP_MOV_64 } };
+    return tab[s][d];
+}
+
+int red_class(ek_type t) {
+    switch (cls_of(t)) {
+        case C_F32: return EK_RC_F32; case C_F64: return EK_RC_F64;
+        case C_I32: return EK_RC_I32; case C_U32: return EK_RC_U32;
+        case C_I64: return EK_RC_I64; default: return EK_RC_U64;
+    }
+}
+
+uint64_t red_identity(int kind, int cls) {
+    auto f32 = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint64_t) u; };
+    auto f64 = [](double f) { uint64_t u; memcpy(&u, &f, 8); return u; };
+    switch (cls) {
+        case EK_RC_F32: return kind == EK_RED_SUM ? f32(0.f) : kind == EK_RED_PROD ? f32(1.f) : kind == EK_RED_MIN ? 0x7f800000ull : 0xff800000ull;
+        case EK_RC_F64: return kind == EK_RED_SUM ? f64(0.0) : kind == EK_RED_PROD ? f64(1.0) : kind == EK_RED_MIN ? 0x7ff0000000000000ull : 0xfff0000000000000ull;
+        case EK_RC_I32: return kind == EK_RED_SUM ? 0 : kind == EK_RED_PROD ? 1 : kind == EK_RED_MIN ? 0x7fffffffull : 0x80000000ull;
+        case EK_RC_U32: return kind == EK_RED_SUM ? 0 : kind == EK_RED_PROD ? 1 : kind == EK_RED_MIN ? 0xffffffffull : 0;
+        case EK_RC_I64: return kind == EK_RED_SUM ? 0 : kind == EK_RED_PROD ? 1 : kind == EK_RED_MIN ? 0x7fffffffffffffffull : 0x8000000000000000ull;
+        default:        return kind == EK_RED_SUM ? 0 : kind == EK_RED_PROD ? 1 : kind == EK_RED_MIN ? ~0ull : 0;
+    }
+}
+
+/* ------------------------------------------------------------------ assembler */
+struct Assembler {
+    EkContext &ctx;
+    const Group &g;
+    const std::unordered_set<uint32_t> &forced;
+    bool dry;
+    Assembled out;
+
+    std::unordered_map<uint32_t, Loc> loc;
+    std::unordered_map<uint32_t, uint32_t> last_use;   /* var -> sched position of last consumer */
+    std::unordered_map<uint32_t, uint32_t> epos;       /* var -> emit index */
+    std::unordered_map<uint32_t, uint32_t> last_epos;  /* var -> max emit index among consumers */
+    std::unordered_map<uint64_t, uint32_t> lit32, lit64;
+    std::vector<uint8_t> slot_used;
+    std::unordered_map<uint32_t, uint32_t> red_acc;    /* reduce var -> accumulator slot */
+    uint32_t acc_var = 0;
+    uint32_t cur_e = 0;
+
+    Assembler(EkContext &c, const Group &gr, const std::unordered_set<uint32_t> &f, bool d)
+        : ctx(c), g(gr), forced(f), dry(d) {}
+
+    const EkVariable &var(uint32_t i) const { return ctx.vars[i]; }
+    bool wide() const { return g.size > 1; }
+
+    uint32_t lit_word(uint32_t w) {
+        auto it = lit32.find(w);
+        if (it != lit32.end()) return it->second;
+        uint32_t idx = (uint32_t) out.lits.size();
+        out.lits.push_back(w);
+        lit32[w] = idx;
+        return idx;
+    }
+    uint32_t lit_pair(uint64_t w) {
+        auto it = lit64.find(w);
+        if (it != lit64.end()) return it->second;
+        uint32_t idx = (uint32_t) out.lits.size();
+        out.lits.push_back((uint32_t) w); out.lits.push_back((uint32_t) (w >> 32));
+        lit64[w] = idx;
+        return idx;
+    }
+    /* argument words live after the literals; final uniform index = n_lit + argw (patched in finish) */
+    uint32_t arg_ptr(uint32_t var_idx, bool output) {
+        uint32_t idx = (uint32_t) out.argw.size();
+        out.argw.push_back(0); out.argw.push_back(0);
+        out.ptr_fix.push_back({ idx, var_idx, output });
+        return idx;
+    }
+
+    uint32_t alloc_slots(uint32_t n) {
+        for (uint32_t s = 0; s + n <= slot_used.size(); ++s) {
+            bool ok = true;
+            for (uint32_t k = 0; k < n; ++k) if (slot_used[s + k]) { ok = false; break; }
+            if (ok) { for (uint32_t k = 0; k < n; ++k) slot_used[s + k] = 1; return s; }
+        }
+        uint32_t s = (uint32_t) slot_used.size();
+        /* keep pairs contiguous: if the last slot is free and n == 2, extend from it */
+        if (n == 2 && s > 0 && !slot_used[s - 1]) { slot_used[s - 1] = 1; slot_used.push_back(1); return s - 1; }
+        for (uint32_t k = 0; k < n; ++k) slot_used.push_back(1);
+        return s;
+    }
+    void free_slots(uint32_t s, uint32_t n) { for (uint32_t k = 0; k < n; ++k) slot_used[s + k] = 0; }
+
+    /* uniform codes are encoded with a marker and rebased in finish():
+       literal word i -> 0x8000 | i ; argument word j -> 0x8000 | 0x2000 | j (rebased by n_lit) */
+    static uint16_t uni_lit(uint32_t i) { return (uint16_t) (0x8000u | i); }
+    static uint16_t uni_arg(uint32_t j) { return (uint16_t) (0x8000u | 0x2000u | j); }
+    static uint16_t staged_code(uint32_t unit) { return (uint16_t) (0x4000u | unit); }
+
+    bool fail(const std::string &m) { if (out.error.empty()) out.error = m; return false; }
+
+    uint16_t operand(uint32_t v) {
+        if (v == acc_var) return EK_OPND_ACC;
+        auto it = loc.find(v);
+        if (it == loc.end()) { fail("internal: operand " + std::to_string(v) + " has no location"); return EK_OPND_NONE; }
+        switch (it->second.kind) {
+            case Loc::UNI: return it->second.idx;
+            case Loc::STAGED: return staged_code(it->second.idx);
+            case Loc::SLOT: return it->second.idx;
+            default: fail("internal: operand " + std::to_string(v) + " not materialised"); return EK_OPND_NONE;
+        }
+    }
+
+    void release(uint32_t v, uint32_t pos) {
+        auto it = last_use.find(v);
+        if (it == last_use.end() || it->second != pos) return;
+        auto l = loc.find(v);
+        if (l != loc.end() && l->second.kind == Loc::SLOT) {
+            free_slots(l->second.idx, ek_is_64(var(v).type) ? 2 : 1);
+            l->second.kind = Loc::NONE;
+        }
+    }
+
+    EkInstr mk(int op, uint16_t a = EK_OPND_NONE, uint16_t b = EK_OPND_NONE, uint16_t c = EK_OPND_NONE,
+               uint32_t nargs = 0, uint32_t imm = 0) {
+        EkInstr in;
+        in.op = (uint16_t) op; in.dst = 0; in.a = a; in.b = b; in.c = c;
+        in.flags = EKF_NARG(nargs); in.imm = imm;
+        return in;
+    }
+
+    /* give the value of `v` (just produced into the accumulator by `in`) a home */
+    void place_result(EkInstr &in, uint32_t v, bool produces) {
+        if (!produces) return;
+        const EkVariable &vv = var(v);
+        bool is64 = ek_is_64(vv.type);
+        if (is64) in.flags |= EKF_R64;
+        auto le = last_epos.find(v);
+        bool needs_slot = le != last_epos.end() && le->second > cur_e + 1;
+        if (needs_slot) {
+            uint32_t s = alloc_slots(is64 ? 2 : 1);
+            in.flags |= EKF_ST; in.dst = (uint16_t) s;
+            loc[v] = { Loc::SLOT, (uint16_t) s };
+        } else {
+            loc[v] = { Loc::PENDING, 0 };
+        }
+    }
+
+    bool run() {
+        /* ---- pass 1: classify inputs, count uses ---- */
+        uint32_t e = 0;
+        std::vector<uint32_t> emits(g.sched.size(), 0);
+        for (size_t i = 0; i < g.sched.size(); ++i) {
+            uint32_t idx = g.sched[i];
+            const EkVariable &v = var(idx);
+            bool is_input = v.data != nullptr || v.direct_pointer || boundary_input(idx);
+            bool emitting;
+            if (is_input) emitting = false;
+            else if (v.op == EK_OP_LITERAL) emitting = lit_emits(idx);
+            else emitting = true;
+            if (emitting) {
+                ++e;
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t d = v.dep[k];
+                    if (d < EK_REG_RESERVED) continue;
+                    last_use[d] = (uint32_t) i;
+                    last_epos[d] = e;
+                }
+            }
+            emits[i] = e;
+            epos[idx] = e;
+        }
+
+        /* ---- staged inputs / scalars / literals ---- */
+        uint32_t unit = 0;
+        std::vector<std::pair<uint32_t, size_t>> unpack;   /* (var, sched pos) */
+        for (size_t i = 0; i < g.sched.size(); ++i) {
+            uint32_t idx = g.sched[i];
+            const EkVariable &v = var(idx);
+            bool binput = boundary_input(idx);
+            if (v.direct_pointer) {
+                uint32_t a = arg_ptr(idx, false);
+                loc[idx] = { Loc::UNI, uni_arg(a) };
+            } else if (v.data != nullptr || binput) {
+                size_t es = ek_type_size(v.type);
+                if (v.size == 1 || !wide()) {
+                    if (out.scalars.size() >= EK_MAX_SCALAR) return fail("too many scalar inputs in one kernel (limit " + std::to_string(EK_MAX_SCALAR) + ")");
+                    uint32_t sidx = (uint32_t) out.scalars.size();
+                    out.scalars.push_back({ idx });
+                    loc[idx] = { Loc::UNI, (uint16_t) (0x8000u | 0x1000u | (2u * sidx)) };   /* rebased in finish */
+                } else {
+                    if (v.size != g.size) return fail("encountered arrays of incompatible size");
+                    if (out.staged.size() >= EK_MAX_STAGED) return fail("too many input arrays in one kernel (limit " + std::to_string(EK_MAX_STAGED) + "); call cuda_eval() earlier");
+                    uint32_t units = es == 8 ? 2 : 1;
+                    out.staged.push_back({ idx, (uint16_t) unit, (uint8_t) es });
+                    loc[idx] = { Loc::STAGED, (uint16_t) unit };
+                    if (es != 4) unpack.push_back({ idx, i });
+                    unit += units;
+                    out.bytes_in += (uint64_t) v.size * es;
+                }
+            } else if (v.op == EK_OP_LITERAL) {
+                if (ek_is_64(v.type)) loc[idx] = { Loc::UNI, uni_lit(lit_pair(v.imm)) };
+                else loc[idx] = { Loc::UNI, uni_lit(lit_word((uint32_t) v.imm)) };
+            }
+        }
+        out.n_in_units = unit;
+
+        /* ---- reduction accumulators persist across tiles: reserve their slots up front ---- */
+        for (uint32_t idx : g.sched) {
+            const EkVariable &v = var(idx);
+            if (v.data != nullptr || boundary_input(idx) || !is_reduce(v.op)) continue;
+            bool w64 = ek_is_64(var(v.dep[0]).type) && v.op != EK_OP_ALL && v.op != EK_OP_ANY && v.op != EK_OP_COUNT;
+            red_acc[idx] = alloc_slots(w64 ? 2 : 1);
+        }
+
+        /* ---- body prologue: unpack non-32-bit staged inputs into slots ---- */
+        for (auto &u : unpack) {
+            uint32_t idx = u.first;
+            const EkVariable &v = var(idx);
+            int op;
+            switch (v.type) {
+                case EK_BOOL: case EK_UINT8: op = DOP_LD_U8; break;
+                case EK_INT8: op = DOP_LD_S8; break;
+                case EK_UINT16: op = DOP_LD_U16; break;
+                case EK_INT16: op = DOP_LD_S16; break;
+                case EK_FLOAT16: return fail("Float16 arrays are not supported");
+                default: op = DOP_LD_64; break;
+            }
+            EkInstr in = mk(op, staged_code(loc[idx].idx));
+            bool is64 = ek_is_64(v.type);
+            uint32_t s = alloc_slots(is64 ? 2 : 1);
+            in.flags |= EKF_ST | (is64 ? EKF_R64 : 0); in.dst = (uint16_t) s;
+            loc[idx] = { Loc::SLOT, (uint16_t) s };
+            out.body.push_back(in);
+            if (last_use.find(idx) == last_use.end()) free_slots(s, is64 ? 2 : 1);
+        }
+        acc_var = 0;
+
+        /* ---- pass 2: emit ---- */
+        for (size_t i = 0; i < g.sched.size(); ++i) {
+            uint32_t idx = g.sched[i];
+            const EkVariable &v = var(idx);
+            if (v.data != nullptr || v.direct_pointer || boundary_input(idx)) continue;
+            if (v.op == EK_OP_LITERAL && !lit_emits(idx)) continue;
+            cur_e = emits[i];
+            if (!emit_var(idx, (uint32_t) i)) return false;
+        }
+        return finish();
+    }
+
+    /* literals are immediates; they only become instructions when they must be materialised
+       (externally referenced root of this sweep's size, e.g. `Float c = 2.f; c.eval()`) */
+    bool lit_emits(uint32_t idx) const {
+        const EkVariable &v = var(idx);
+        return v.op == EK_OP_LITERAL && v.size == g.size && ((v.ref_ext > 0 && !v.side_effect) || forced.count(idx));
+    }
+
+    /* a variable that is computed by an EARLIER launch of this eval (reduction result or forced
+       scalar) and is therefore an input here */
+    bool boundary_input(uint32_t idx) const {
+        if (var(idx).data != nullptr) return false;
+        return forced.count(idx) && g.visited.count(idx) == 0;
+    }
+
+    bool emit_var(uint32_t idx, uint32_t pos) {
+        const EkVariable &v = var(idx);
+        ek_op op = v.op;
+        ek_type t = v.type;
+        bool is64 = ek_is_64(t);
+        out.n_arith++;
+
+        auto opflags = [&](EkInstr &in, uint32_t a, uint32_t b, uint32_t c) {
+            if (a && ek_is_64(var(a).type)) in.flags |= EKF_A64;
+            if (b && ek_is_64(var(b).type)) in.flags |= EKF_B64;
+            if (c && ek_is_64(var(c).type)) in.flags |= EKF_C64;
+        };
+        auto after = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+            if (a) release(a, pos);
+            if (b) release(b, pos);
+            if (c) release(c, pos);
+            if (d) release(d, pos);
+        };
+
+        if (t == EK_FLOAT16) return fail("Float16 arithmetic is not supported");
+
+        if (is_reduce(op)) {
+            uint32_t x = v.dep[0];
+            ek_type xt = var(x).type;
+            int kind, cls = red_class(xt);
+            switch (op) {
+                case EK_OP_HSUM: kind = EK_RED_SUM; break;
+                case EK_OP_HPROD: kind = EK_RED_PROD; break;
+                case EK_OP_HMAX: kind = EK_RED_MAX; break;
+                case EK_OP_HMIN: kind = EK_RED_MIN; break;
+                case EK_OP_ALL: kind = EK_RED_MIN; cls = EK_RC_U32; break;
+                case EK_OP_ANY: kind = EK_RED_MAX; cls = EK_RC_U32; break;
+                default: kind = EK_RED_SUM; cls = EK_RC_U32; break;   /* COUNT */
+            }
+            if (out.n_red >= EK_MAX_RED) return fail("too many reductions in one kernel");
+            bool w64 = cls >= EK_RC_F64;
+            uint32_t ridx = out.n_red++;
+            uint32_t acc = red_acc[idx];                 /* reserved in run(); never freed */
+            uint64_t ident = red_identity(kind, cls);
+            EkInstr ini = mk(w64 ? DOP_MOV_64 : DOP_MOV_32, w64 ? uni_lit(lit_pair(ident)) : uni_lit(lit_word((uint32_t) ident)),
+                             EK_OPND_NONE, EK_OPND_NONE, 1);
+            ini.flags |= EKF_ST | (w64 ? (EKF_R64 | EKF_A64) : 0); ini.dst = (uint16_t) acc;
+            out.init.push_back(ini);
+            EkInstr in = mk(DOP_RACC, operand(x), EK_OPND_NONE, EK_OPND_NONE, 1, (uint32_t) kind | ((uint32_t) cls << 8));
+            if (w64) in.flags |= EKF_A64;
+            in.dst = (uint16_t) acc;
+            out.body.push_back(in);
+            uint32_t pa = arg_ptr(idx, true);
+            out.outputs.push_back({ idx, pa, 8 });
+            EkInstr fi = mk(DOP_RFIN, (uint16_t) acc, EK_OPND_NONE, EK_OPND_NONE, 1,
+                            (uint32_t) kind | ((uint32_t) cls << 8) | (ridx << 16));
+            if (w64) fi.flags |= EKF_A64;
+            fi.dst = uni_arg(pa) & 0x7fffu;      /* plain uniform index (rebased in finish) */
+            out.fini.push_back(fi);
+            after(x, 0, 0, 0);
+            return out.error.empty();
+        }
+
+        EkInstr in;
+        bool produces = true;
+        uint32_t d0 = v.dep[0], d1 = v.dep[1], d2 = v.dep[2], d3 = v.dep[3];
+
+        switch (op) {
+            case EK_OP_INDEX:
+                in = mk(DOP_INDEX);
+                break;
+            case EK_OP_LITERAL:
+                in = mk(is64 ? DOP_MOV_64 : DOP_MOV_32, loc[idx].idx, EK_OPND_NONE, EK_OPND_NONE, 1);
+                if (is64) in.flags |= EKF_A64;
+                break;
+            case EK_OP_CVT: case EK_OP_FLOOR2INT: case EK_OP_CEIL2INT: {
+                ek_type st = var(d0).type;
+                int dop;
+                if (t == EK_BOOL && st != EK_BOOL) {
+                    if (ek_is_float(st) || ek_is_64(st)) return fail("conversion to bool from this type is not supported");
+                    dop = DOP_NEZ_32;
+                } else dop = pick_cvt(st, t);
+                if (dop < 0) return fail("unsupported conversion");
+                uint32_t mode = op == EK_OP_FLOOR2INT ? EK_RM : op == EK_OP_CEIL2INT ? EK_RP : EK_RZ;
+                in = mk(dop, operand(d0), EK_OPND_NONE, EK_OPND_NONE, 1, mode);
+                opflags(in, d0, 0, 0);
+            } break;
+            case EK_OP_BITCAST: {
+                if (ek_type_size(var(d0).type) != ek_type_size(t)) return fail("bitcast between types of different size");
+                in = mk(is64 ? DOP_MOV_64 : DOP_MOV_32, operand(d0), EK_OPND_NONE, EK_OPND_NONE, 1);
+                opflags(in, d0, 0, 0);
+            } break;
+            case EK_OP_GATHER: {
+                const EkVariable &pv = var(d0);
+                uint32_t stride = (uint32_t) (v.imm & 0x7fffu);
+                if (stride == 0) stride = (uint32_t) ek_type_size(t);
+                ek_type it = var(d1).type;
+                bool sgn = ek_is_signed(it);
+                int dop;
+                bool smem_table = false;
+                switch (t) {
+                    case EK_BOOL: case EK_UINT8: dop = DOP_GATHER_U8; break;
+                    case EK_INT8: dop = DOP_GATHER_S8; break;
+                    case EK_UINT16: dop = DOP_GATHER_U16; break;
+                    case EK_INT16: dop = DOP_GATHER_S16; break;
+                    case EK_INT32: case EK_UINT32: case EK_FLOAT32: dop = DOP_GATHER_32; break;
+                    default: dop = DOP_GATHER_64; break;
+                }
+                /* small 32-bit tables are staged in shared memory once per CTA */
+                if (dop == DOP_GATHER_32 && stride == 4 && v.extra_dep >= EK_REG_RESERVED && wide() && !ek_is_64(it) && !sgn) {
+                    const EkVariable &tv = var(v.extra_dep);
+                    if (tv.data == pv.data && tv.size <= 4096 && ek_type_size(tv.type) == 4) smem_table = true;
+                }
+                uint32_t pa = loc[d0].idx;   /* uniform code of the pointer words */
+                if (smem_table) {
+                    uint32_t count = (uint32_t) var(v.extra_dep).size;
+                    uint32_t di = (uint32_t) out.argw.size();
+                    out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(1); out.argw.push_back(pa);
+                    out.extra_bytes += (count * 4 + 15) & ~15u;
+                    out.init.push_back(mk(DOP_SMEM_LOAD_TABLE, EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, 0x80000000u | di));
+                    in = mk(DOP_GATHER_32_SMEM, operand(d1), operand(d2), EK_OPND_NONE, 2, 0x80000000u | di);
+                } else {
+                    in = mk(dop, operand(d1), operand(d2), EK_OPND_NONE, 2, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
+                    in.flags |= 0x8000u;     /* marker: imm low 16 bits hold a uniform code to rebase */
+                }
+                if (ek_is_64(it)) in.flags |= EKF_A64;
+            } break;
+            case EK_OP_SCATTER: case EK_OP_SCATTER_ADD: {
+                const EkVariable &pv = var(d0);
+                ek_type vt = var(d3).type;
+                uint32_t stride = (uint32_t) ((v.imm >> 32) & 0x7fffu);
+                if (stride == 0) stride = (uint32_t) ek_type_size(vt);
+                ek_type it = var(d1).type;
+                bool sgn = ek_is_signed(it);
+                int dop; bool smem_bins = false;
+                size_t es = ek_type_size(vt);
+                if (op == EK_OP_SCATTER) {
+                    dop = es == 1 ? DOP_SCATTER_8 : es == 2 ? DOP_SCATTER_16 : es == 4 ? DOP_SCATTER_32 : DOP_SCATTER_64;
+                } else {
+                    switch (vt) {
+                        case EK_FLOAT32: dop = DOP_SCATTER_ADD_F32; break;
+                        case EK_INT32: case EK_UINT32: dop = DOP_SCATTER_ADD_I32; break;
+                        case EK_FLOAT64: dop = DOP_SCATTER_ADD_F64; break;
+                        case EK_INT64: case EK_UINT64: dop = DOP_SCATTER_ADD_I64; break;
+                        default: return fail("scatter_add: unsupported type");
+                    }
+                    if (es == 4 && stride == 4 && v.extra_dep >= EK_REG_RESERVED && wide() && !ek_is_64(it) && !sgn) {
+                        const EkVariable &tv = var(v.extra_dep);
+                        if (tv.data == pv.data && tv.size <= 1024 && ek_type_size(tv.type) == 4) smem_bins = true;
+                    }
+                }
+                uint32_t pa = loc[d0].idx;
+                if (smem_bins) {
+                    uint32_t count = (uint32_t) var(v.extra_dep).size;
+                    uint32_t copies = std::max(1u, std::min(16u, 4096u / count));
+                    uint32_t di = (uint32_t) out.argw.size();
+                    out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(copies); out.argw.push_back(pa);
+                    out.extra_bytes += (count * copies * 4 + 15) & ~15u;
+                    out.init.push_back(mk(DOP_SMEM_ZERO, EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, 0x80000000u | di));
+                    out.fini.push_back(mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SMEM_FLUSH_ADD_F32 : DOP_SMEM_FLUSH_ADD_I32,
+                                          EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, 0x80000000u | di));
+                    in = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SCATTER_ADD_F32_SMEM : DOP_SCATTER_ADD_I32_SMEM,
+                            operand(d1), operand(d3), operand(d2), 3, 0x80000000u | di);
+                } else {
+                    in = mk(dop, operand(d1), operand(d3), operand(d2), 3, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
+                    in.flags |= 0x8000u;
+                }
+                if (ek_is_64(it)) in.flags |= EKF_A64;
+                if (ek_is_64(vt)) in.flags |= EKF_B64;
+                produces = false;
+            } break;
+            case EK_OP_AND: case EK_OP_OR: {
+                ek_type bt = var(d1).type;
+                if (t != EK_BOOL && bt == EK_BOOL) {
+                    /* value & mask / value | mask (cuda.h:545-572): select forms */
+                    uint16_t zero = is64 ? uni_lit(lit_pair(op == EK_OP_AND ? 0ull : ~0ull))
+                                         : uni_lit(lit_word(op == EK_OP_AND ? 0u : 0xffffffffu));
+                    if (op == EK_OP_AND) in = mk(is64 ? DOP_SELECT_64 : DOP_SELECT_32, operand(d1), operand(d0), zero, 3);
+                    else                 in = mk(is64 ? DOP_SELECT_64 : DOP_SELECT_32, operand(d1), zero, operand(d0), 3);
+                    if (is64) in.flags |= EKF_B64 | EKF_C64;
+                    break;
+                }
+            }   /* fall through */
+            default: {
+                int arity = 0;
+                uint32_t deps[3] = { d0, d1, d2 };
+                if (op >= EK_OP_MOV && op <= EK_OP_CTZ) arity = 1;
+                else if (op >= EK_OP_ADD && op <= EK_OP_MUL_NZ) arity = 2;
+                else if (op == EK_OP_FMA || op == EK_OP_SELECT || op == EK_OP_FMA_NZ) arity = 3;
+                else return fail(std::string("unsupported op ") + ek_op_name(op));
+                ek_type at = var(d0).type;
+                int dop = pick_op(op, t, at);
+                if (dop < 0) return fail(std::string("op ") + ek_op_name(op) + " not supported for type " + ek_type_name(op >= EK_OP_GT && op <= EK_OP_NE ? at : t));
+                in = mk(dop, operand(deps[0]), arity > 1 ? operand(deps[1]) : EK_OPND_NONE,
+                        arity > 2 ? operand(deps[2]) : EK_OPND_NONE, arity);
+                opflags(in, deps[0], arity > 1 ? deps[1] : 0, arity > 2 ? deps[2] : 0);
+                /* 64-bit shifts take a 32-bit count (cuda.h:503-505) */
+                if ((op == EK_OP_SHL || op == EK_OP_SHR) && is64 && ek_is_64(var(d1).type)) {
+                    /* count operand arrives as 64-bit: only its low plane is read */
+                    in.flags &= ~EKF_B64;
+                }
+            } break;
+        }
+
+        int nop = -1;
+        bool arith_narrow = (op >= EK_OP_NEG && op <= EK_OP_ABS) || (op >= EK_OP_ADD && op <= EK_OP_SHR) ||
+                            op == EK_OP_FMA || op == EK_OP_NOT || op == EK_OP_CVT || op == EK_OP_FLOOR2INT || op == EK_OP_CEIL2INT;
+        if (arith_narrow) nop = norm_op(t);
+
+        if (nop >= 0 && produces) {
+            if (is64) in.flags |= EKF_R64;
+            out.body.push_back(in);
+            acc_var = 0;
+            EkInstr nn = mk(nop, EK_OPND_ACC, EK_OPND_NONE, EK_OPND_NONE, 1);
+            after(d0, d1, d2, d3);
+            place_result(nn, idx, true);
+            out.body.push_back(nn);
+            acc_var = idx;
+        } else {
+            after(d0, d1, d2, d3);
+            place_result(in, idx, produces);
+            out.body.push_back(in);
+            if (produces) acc_var = idx;
+        }
+
+        /* ---- output store (jit.cu:1165-1205) ---- */
+        if (produces) {
+            bool store = (!v.side_effect && v.ref_ext > 0 && v.size == g.size) || forced.count(idx);
+            if (store) {
+                size_t es = ek_type_size(t);
+                uint32_t pa = arg_ptr(idx, true);
+                out.outputs.push_back({ idx, pa, std::max<size_t>(v.size * es, 8) });
+                int sop = es == 1 ? DOP_ST_8 : es == 2 ? DOP_ST_16 : es == 4 ? DOP_ST_32 : DOP_ST_64;
+                EkInstr st = mk(sop, EK_OPND_ACC, EK_OPND_NONE, EK_OPND_NONE, 1, uni_arg(pa) & 0x7fffu);
+                if (es == 8) st.flags |= EKF_A64 | EKF_R64;
+                st.flags |= 0x4000u;      /* marker: imm holds a uniform index to rebase */
+                out.body.push_back(st);
+                out.bytes_out += (uint64_t) v.size * es;
+            }
+        }
+        return out.error.empty();
+    }
+
+    /* rebase uniform indices now that the literal count is known:
+       pool = [literals | argument words | scalar pairs] */
+    bool finish() {
+        uint32_t n_lit = (uint32_t) out.lits.size();
+        uint32_t n_arg = (uint32_t) out.argw.size();
+        if (n_arg > EK_MAX_ARGW) return fail("too many kernel arguments; call cuda_eval() earlier");
+        if (n_lit + n_arg + 2 * out.scalars.size() >= 0x1000u) return fail("uniform pool overflow");
+        out.n_tmp = (uint32_t) slot_used.size();
+        auto rebase_code = [&](uint16_t code) -> uint16_t {
+            if (code == EK_OPND_NONE || code == EK_OPND_ACC) return code;
+            if (code & 0x8000u) {
+                uint32_t i = code & 0x0fffu;
+                if (code & 0x2000u) return (uint16_t) (0x8000u | (n_lit + i));
+                if (code & 0x1000u) return (uint16_t) (0x8000u | (n_lit + n_arg + i));
+                return (uint16_t) (0x8000u | i);
+            }
+            if ((code & 0xC000u) == 0x4000u) return (uint16_t) (out.n_tmp + (code & 0x3fffu));
+            return code;
+        };
+        auto fix = [&](std::vector<EkInstr> &v) {
+            for (EkInstr &in : v) {
+                in.a = rebase_code(in.a); in.b = rebase_code(in.b); in.c = rebase_code(in.c);
+                if (in.flags & 0x8000u) {           /* gather/scatter: low 16 bits = uniform code of pointer */
+                    uint16_t code = (uint16_t) (in.imm & 0xffffu);
+                    in.imm = (in.imm & 0xffff0000u) | (rebase_code(code) & 0x7fffu);
+                    in.flags &= ~0x8000u;
+                }
+                if (in.flags & 0x4000u) {           /* stores: imm = argument-word uniform index */
+                    in.imm = n_lit + (in.imm & 0x0fffu);
+                    in.flags &= ~0x4000u;
+                }
+                if (in.imm & 0x80000000u) {
+                    int op = in.op;
+                    if (op == DOP_SMEM_ZERO || op == DOP_SMEM_LOAD_TABLE || op == DOP_SMEM_FLUSH_ADD_F32 ||
+                        op == DOP_SMEM_FLUSH_ADD_I32 || op == DOP_GATHER_32_SMEM ||
+                        op == DOP_SCATTER_ADD_F32_SMEM || op == DOP_SCATTER_ADD_I32_SMEM)
+                        in.imm = n_lit + (in.imm & 0x7fffffffu);     /* descriptor index */
+                }
+                if (in.op == DOP_RFIN) in.dst = (uint16_t) (n_lit + (in.dst & 0x0fffu));
+            }
+        };
+        fix(out.init); fix(out.body); fix(out.fini);
+        /* descriptors hold the uniform code of their pointer in word 3: convert to plain index */
+        for (EkInstr &in : out.init) {
+            if (in.op == DOP_SMEM_ZERO || in.op == DOP_SMEM_LOAD_TABLE) {
+                uint32_t di = in.imm - n_lit;
+                uint16_t code = (uint16_t) out.argw[di + 3];
+                if (code & 0x8000u) out.argw[di + 3] = rebase_code(code) & 0x7fffu;
+            }
+        }
+        return out.error.empty();
+    }
+};
+
+/* ------------------------------------------------------------------ planning */
+struct Planner {
+    EkContext &ctx;
+    std::unordered_map<uint32_t, uint32_t> phase_memo;
+    std::unordered_set<uint32_t> forced;      /* variables that must be materialised */
+    std::map<std::pair<uint32_t, size_t>, Group> groups;   /* (phase, size) */
+
+    explicit Planner(EkContext &c) : ctx(c) {}
+
+    size_t sweep_size(uint32_t idx) const {
+        const EkVariable &v = ctx.vars[idx];
+        return is_reduce(v.op) ? ctx.vars[v.dep[0]].size : v.size;
+    }
+    bool is_boundary(uint32_t d, uint32_t consumer) const {
+        const EkVariable &dv = ctx.vars[d], &cv = ctx.vars[consumer];
+        if (dv.data != nullptr || dv.direct_pointer) return false;
+        if (is_reduce(dv.op)) return true;
+        size_t csize = is_reduce(cv.op) ? ctx.vars[cv.dep[0]].size : cv.size;
+        return dv.size == 1 && csize > 1 && dv.op != EK_OP_LITERAL;
+    }
+
+    /* an externally referenced root of an earlier phase is stored by its own launch
+       (jit.cu:1165-1169) and can simply be read back instead of being recomputed */
+    bool stored_earlier(uint32_t d, uint32_t group_phase) {
+        const EkVariable &dv = ctx.vars[d];
+        if (dv.data != nullptr || dv.direct_pointer || dv.op == EK_OP_LITERAL) return false;
+        if (dv.ref_ext == 0 || dv.side_effect) return false;
+        return phase(d) < group_phase;
+    }
+
+    uint32_t phase(uint32_t root) {
+        /* iterative post-order (tapes can be 10k nodes deep) */
+        std::vector<std::pair<uint32_t, int>> stack { { root, 0 } };
+        while (!stack.empty()) {
+            auto &top = stack.back();
+            uint32_t idx = top.first;
+            const EkVariable &v = ctx.vars[idx];
+            if (phase_memo.count(idx)) { stack.pop_back(); continue; }
+            if (v.data != nullptr || v.direct_pointer || v.op == EK_OP_LITERAL) { phase_memo[idx] = 0; stack.pop_back(); continue; }
+            if (top.second < 4) {
+                uint32_t d = v.dep[top.second++];
+                if (d >= EK_REG_RESERVED && !phase_memo.count(d)) stack.push_back({ d, 0 });
+                continue;
+            }
+            uint32_t p = 0;
+            for (int k = 0; k < 4; ++k) {
+                uint32_t d = v.dep[k];
+                if (d < EK_REG_RESERVED) continue;
+                p = std::max(p, phase_memo[d] + (is_boundary(d, idx) ? 1u : 0u));
+            }
+            phase_memo[idx] = p;
+            stack.pop_back();
+        }
+        return phase_memo[root];
+    }
+
+    void add_root(uint32_t idx, std::vector<uint32_t> &work) {
+        uint32_t p = phase(idx);
+        Group &g = groups[{ p, sweep_size(idx) }];
+        g.phase = p; g.size = sweep_size(idx);
+        if (g.visited.count(idx)) return;
+        /* DFS post-order, heavier subtree first (jit.cu:1385-1416) */
+        struct Frame { uint32_t idx; uint32_t deps[4]; int n; int i; };
+        std::vector<Frame> stack;
+        auto push = [&](uint32_t i) {
+            if (g.visited.count(i)) return;
+            g.visited.insert(i);
+            Frame f; f.idx = i; f.n = 0; f.i = 0;
+            const EkVariable &v = ctx.vars[i];
+            if (v.data == nullptr && !v.direct_pointer) {
+                for (int k = 0; k < 4; ++k) if (v.dep[k] >= EK_REG_RESERVED) f.deps[f.n++] = v.dep[k];
+                std::stable_sort(f.deps, f.deps + f.n, [&](uint32_t a, uint32_t b) {
+                    return ctx.vars[a].subtree_size > ctx.vars[b].subtree_size; });
+            }
+            stack.push_back(f);
+        };
+        push(idx);
+        while (!stack.empty()) {
+            Frame &f = stack.back();
+            if (f.i < f.n) {
+                uint32_t d = f.deps[f.i++];
+                if (is_boundary(d, f.idx) || stored_earlier(d, g.phase)) {
+                    /* produced by an earlier launch: becomes an input here and a root there */
+                    if (!forced.count(d)) { forced.insert(d); work.push_back(d); }
+                    if (!g.visited.count(d)) { /* appears in the schedule as an input */
+                        g.sched.push_back(d);
+                        g.visited.insert(d);      /* NB: visited but "boundary" -- see boundary set */
+                        boundary_of[&g].insert(d);
+                    }
+                } else push(d);
+                continue;
+            }
+            g.sched.push_back(f.idx);
+            stack.pop_back();
+        }
+        g.roots.push_back(idx);
+    }
+    std::unordered_map<const Group *, std::unordered_set<uint32_t>> boundary_of;
+};
+
+size_t smem_layout(const Assembled &a, Config &cfg, size_t n_uni) {
+    size_t off = (n_uni * 4 + 15) & ~(size_t) 15;
+    cfg.off_bar = (uint32_t) off; off += 8 * 8 + 33 * 8;
+    off = (off + 15) & ~(size_t) 15;
+    size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
+    cfg.prog_in_smem = n_prog * 16 <= 24 * 1024;
+    cfg.off_prog = (uint32_t) off;
+    if (cfg.prog_in_smem) off += n_prog * 16;
+    cfg.off_extra = (uint32_t) off; off += a.extra_bytes;
+    off = (off + 1023) & ~(size_t) 1023;
+    cfg.off_slots = (uint32_t) off;
+    size_t slot_bytes = (size_t) cfg.T * cfg.V * 4;
+    off += slot_bytes * (a.n_tmp + (size_t) cfg.stages * a.n_in_units);
+    cfg.smem = off;
+    return off;
+}
+
+bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &cfg, std::string &err) {
+    size_t n_uni = a.lits.size() + a.argw.size() + 2 * a.scalars.size();
+    size_t budget = ctx.smem_optin;                 /* per CTA (227 KB) */
+    size_t per_sm = 228 * 1024 - 1024;              /* per SM, minus the 1 KB per-CTA reservation */
+    struct Cand { int V; uint32_t T; uint32_t stages; uint32_t want_ctas; };
+    static const Cand cands[] = {
+        { 8, 256, 2, 2 }, { 8, 256, 3, 1 }, { 8, 256, 2, 1 }, { 8, 128, 2, 2 }, { 8, 128, 2, 1 },
+        { 4, 128, 2, 1 }, { 4, 64, 2, 1 }, { 4, 32, 2, 1 } };
+    if (n <= 4096) {
+        /* tiny sweeps (incl. the size-1 scalar groups): one small CTA */
+        static const Cand small[] = { { 4, 32, 2, 1 }, { 4, 128, 2, 1 }, { 8, 256, 2, 1 } };
+        uint32_t pick = n <= 128 ? 0 : n <= 512 ? 1 : 2;
+        for (uint32_t k = pick; k < 3; ++k) {
+            cfg.V = small[k].V; cfg.T = small[k].T; cfg.stages = 2; cfg.ctas_per_sm = 1;
+            if (smem_layout(a, cfg, n_uni) <= budget) return true;
+        }
+    }
+    for (const Cand &c : cands) {
+        cfg.V = c.V; cfg.T = c.T; cfg.stages = a.n_in_units ? c.stages : 2; cfg.ctas_per_sm = c.want_ctas;
+        size_t need = smem_layout(a, cfg, n_uni);
+        if (need > budget) continue;
+        if ((need + 1024) * c.want_ctas > per_sm + 1024) continue;
+        return true;
+    }
+    err = "expression too large for one kernel (" + std::to_string(a.n_tmp) + " live values, " +
+          std::to_string(a.n_in_units) + " input streams); insert cuda_eval() to split it";
+    return false;
+}
+
+uint64_t fnv1a(const uint8_t *p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+void lookup_program(EkContext &ctx, const Assembled &a, const EkInstr *&d_prog, const uint32_t *&d_lit) {
+    std::vector<uint8_t> key;
+    auto append = [&](const void *p, size_t n) { const uint8_t *b = (const uint8_t *) p; key.insert(key.end(), b, b + n); };
+    uint32_t hdr[3] = { (uint32_t) a.init.size(), (uint32_t) a.body.size(), (uint32_t) a.fini.size() };
+    append(hdr, sizeof(hdr));
+    append(a.init.data(), a.init.size() * sizeof(EkInstr));
+    append(a.body.data(), a.body.size() * sizeof(EkInstr));
+    append(a.fini.data(), a.fini.size() * sizeof(EkInstr));
+    append(a.lits.data(), a.lits.size() * 4);
+    uint64_t h = fnv1a(key.data(), key.size());
+    auto &bucket = ctx.programs[h];
+    for (auto &e : bucket) if (e.key == key) { d_prog = e.d_prog; d_lit = e.d_lit; return; }
+    EkProgramCacheEntry e;
+    e.key = key;
+    size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
+    std::vector<EkInstr> all;
+    all.insert(all.end(), a.init.begin(), a.init.end());
+    all.insert(all.end(), a.body.begin(), a.body.end());
+    all.insert(all.end(), a.fini.begin(), a.fini.end());
+    ek_cuda_check(cudaMalloc(&e.d_prog, std::max<size_t>(n_prog, 1) * sizeof(EkInstr)));
+    ek_cuda_check(cudaMalloc(&e.d_lit, std::max<size_t>(a.lits.size(), 1) * 4));
+    /* synchronous copies from pageable memory: only on a cache miss */
+    if (n_prog) ek_cuda_check(cudaMemcpy(e.d_prog, all.data(), n_prog * sizeof(EkInstr), cudaMemcpyHostToDevice));
+    if (!a.lits.empty()) ek_cuda_check(cudaMemcpy(e.d_lit, a.lits.data(), a.lits.size() * 4, cudaMemcpyHostToDevice));
+    d_prog = e.d_prog; d_lit = e.d_lit;
+    bucket.push_back(std::move(e));
+}
+
+const char *dop_name(uint16_t op) {
+    static const char *names[] = {
+#define X(n) #n,
+        EK_DOPS(X)
+#undef X
+    };
+    return op < DOP__COUNT ? names[op] : "?";
+}
+
+std::string opnd_str(uint16_t c, uint32_t n_tmp) {
+    if (c == EK_OPND_NONE) return "-";
+    if (c == EK_OPND_ACC) return "acc";
+    if (c & 0x8000u) return "u" + std::to_string(c & 0x7fffu);
+    if (c >= n_tmp) return "in" + std::to_string(c - n_tmp);
+    return "s" + std::to_string(c);
+}
+
+void dump_program(std::ostream &os, const Assembled &a, const Group &g) {
+    os << "sweep phase=" << g.phase << " n=" << g.size << " in=" << a.staged.size() << " scalars=" << a.scalars.size()
+       << " out=" << a.outputs.size() << " ops=" << a.n_arith << " tmp_slots=" << a.n_tmp << " lits=" << a.lits.size() << "\n";
+    auto sec = [&](const char *name, const std::vector<EkInstr> &v) {
+        for (const EkInstr &in : v) {
+            os << "  " << name << " " << dop_name(in.op) << " a=" << opnd_str(in.a, a.n_tmp) << " b=" << opnd_str(in.b, a.n_tmp)
+               << " c=" << opnd_str(in.c, a.n_tmp);
+            if (in.flags & EKF_ST) os << " -> s" << in.dst;
+            os << " imm=0x" << std::hex << in.imm << std::dec << "\n";
+        }
+    };
+    sec("init", a.init); sec("body", a.body); sec("fini", a.fini);
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------ eval */
+static int eval_impl(bool dry, std::string *dump) {
+    EkContext &ctx = ek_ctx();
+
+    if (!dry) for (auto cb : ctx.callbacks) cb.first(cb.second);         /* jit.cu:1421-1422 */
+    if (ctx.live.empty()) {
+        if (!dry) { for (uint32_t idx : ctx.dirty) if (idx < ctx.vars.size()) ctx.vars[idx].dirty = false; ctx.dirty.clear(); }
+        return 0;
+    }
+    if (!dry && ek_init() != 0) return -1;
+
+    Planner plan(ctx);
+    std::vector<uint32_t> kept_literals;
+    std::vector<uint32_t> work(ctx.live.begin(), ctx.live.end());
+    std::vector<uint32_t> roots = work;
+    while (!work.empty()) {
+        uint32_t idx = work.back(); work.pop_back();
+        const EkVariable &v = ctx.vars[idx];
+        if (!v.used) continue;
+        if (v.data != nullptr && !v.side_effect) continue;
+        /* literals are immediates: they are only given storage on demand (ek_eval_var) */
+        if (v.op == EK_OP_LITERAL) { kept_literals.push_back(idx); continue; }
+        plan.add_root(idx, work);
+    }
+
+    /* boundary inputs must not be treated as computed in the group that merely reads them */
+    for (auto &kv : plan.groups) {
+        Group &g = kv.second;
+        auto it = plan.boundary_of.find(&g);
+        if (it != plan.boundary_of.end()) for (uint32_t b : it->second) g.visited.erase(b);
+    }
+
+    /* assemble every group first so that user errors leave the trace untouched */
+    std::vector<std::pair<Group *, Assembled>> launches;
+    for (auto &kv : plan.groups) {                       /* ordered by (phase asc, size asc) */
+        Group &g = kv.second;
+        if (g.sched.empty()) continue;
+        Assembler as(ctx, g, plan.forced, dry);
+        if (g.size > 0xffffffffull) { ek_set_error("ek_eval(): arrays with more than 2^32-1 entries are not supported (jit.cu:1066,1090)"); return -1; }
+        if (!as.run()) { ek_set_error("ek_eval(): " + as.out.error); return -1; }
+        launches.emplace_back(&g, std::move(as.out));
+    }
+    /* within a phase launch the largest size first (jit.cu:1450) */
+    std::stable_sort(launches.begin(), launches.end(), [](const auto &a, const auto &b) {
+        if (a.first->phase != b.first->phase) return a.first->phase < b.first->phase;
+        return a.first->size > b.first->size; });
+
+    if (dry) {
+        std::ostringstream oss;
+        for (auto &l : launches) dump_program(oss, l.second, *l.first);
+        if (dump) *dump = oss.str();
+        return 0;
+    }
+
+    for (uint32_t idx : ctx.dirty) if (idx < ctx.vars.size()) ctx.vars[idx].dirty = false;   /* jit.cu:1430-1434 */
+    ctx.live.clear();
+    ctx.dirty.clear();
+    for (uint32_t idx : kept_literals) ctx.live.insert(idx);
+
+    for (auto &l : launches) {
+        Group &g = *l.first;
+        Assembled &a = l.second;
+
+        Config cfg;
+        std::string err;
+        if (!choose_config(ctx, a, g.size, cfg, err)) { ek_set_error("ek_eval(): " + err); return -1; }
+
+        /* allocate outputs (jit.cu:1171-1174) */
+        for (const Output &o : a.outputs) {
+            EkVariable &v = ctx.vars[o.var];
+            if (v.data == nullptr) { v.data = ek_malloc(o.bytes); v.free_data = true; v.subtree_size = 1; }
+        }
+
+        EkSweepArgs args;
+        memset(&args, 0, sizeof(args));
+        lookup_program(ctx, a, args.prog, args.lit);
+        args.n_init = (uint32_t) a.init.size(); args.n_body = (uint32_t) a.body.size(); args.n_fini = (uint32_t) a.fini.size();
+        args.n_lit = (uint32_t) a.lits.size();
+        args.n_argw = (uint32_t) a.argw.size();
+        args.n_scalar = (uint32_t) a.scalars.size();
+        args.n = (uint32_t) g.size;
+        uint32_t tile = cfg.T * cfg.V;
+        args.n_tiles = (uint32_t) ((g.size + tile - 1) / tile);
+        args.n_tmp = a.n_tmp; args.n_in_units = a.n_in_units;
+        args.n_staged = (uint32_t) a.staged.size();
+        args.n_stages = cfg.stages;
+        args.smem_bar_off = cfg.off_bar; args.smem_prog_off = cfg.off_prog;
+        args.smem_extra_off = cfg.off_extra; args.smem_slots_off = cfg.off_slots;
+        args.prog_in_smem = cfg.prog_in_smem ? 1 : 0;
+        args.n_red = a.n_red;
+        args.red_partials = ctx.red_partials; args.red_counters = ctx.red_counters;
+        args.tma_ok = 1;
+        for (size_t k = 0; k < a.staged.size(); ++k) {
+            const EkVariable &v = ctx.vars[a.staged[k].var];
+            if (v.data == nullptr) { ek_set_error("ek_eval(): internal error: staged input without data"); return -1; }
+            args.staged_ptr[k] = v.data;
+            args.staged_unit[k] = a.staged[k].unit;
+            args.staged_esize[k] = a.staged[k].esize;
+            if (((uintptr_t) v.data & 15u) != 0) args.tma_ok = 0;
+        }
+        for (size_t k = 0; k < a.scalars.size(); ++k) {
+            const EkVariable &v = ctx.vars[a.scalars[k].var];
+            if (v.data == nullptr) { ek_set_error("ek_eval(): internal error: scalar input without data"); return -1; }
+            args.scalar_ptr[k] = v.data;
+            args.scalar_type[k] = (uint8_t) v.type;
+        }
+        memcpy(args.argw, a.argw.data(), a.argw.size() * 4);
+        for (const auto &pf : a.ptr_fix) {
+            uint64_t p = (uint64_t) (uintptr_t) ctx.vars[pf.var].data;
+            args.argw[pf.argw] = (uint32_t) p; args.argw[pf.argw + 1] = (uint32_t) (p >> 32);
+        }
+        uint32_t grid = std::min<uint32_t>(args.n_tiles, (uint32_t) ctx.num_sms * cfg.ctas_per_sm);
+        grid = std::max(grid, 1u);
+        if (grid > ctx.max_grid) grid = ctx.max_grid;
+
+        if (ctx.log_level >= 1)
+            fprintf(stderr, "ek_eval(): launching sweep (n=%zu, in=%zu, out=%zu, ops=%u, slots=%u, V=%d, T=%u, stages=%u, grid=%u, smem=%zu)\n",
+                    g.size, a.staged.size() + a.scalars.size(), a.outputs.size(), a.n_arith, a.n_tmp, cfg.V, cfg.T, cfg.stages, grid, cfg.smem);
+        if (ctx.log_level >= 3) { std::ostringstream oss; dump_program(oss, a, g); fputs(oss.str().c_str(), stderr); }
+
+        if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
+        ek_cuda_check(ek_launch_sweep(cfg.V, args, grid, cfg.T, cfg.smem, ctx.stream));
+        if (ctx.timing) {
+            ek_cuda_check(cudaEventRecord(ctx.ev_stop, ctx.stream));
+            ek_cuda_check(cudaEventSynchronize(ctx.ev_stop));
+            float ms = 0; ek_cuda_check(cudaEventElapsedTime(&ms, ctx.ev_start, ctx.ev_stop));
+            ctx.stats.last_kernel_ms = ms; ctx.stats.total_kernel_ms += ms;
+        }
+        ctx.stats.launches++; ctx.stats.sweep_launches++;
+        ctx.stats.ops_evaluated += (uint64_t) a.n_arith * g.size;
+        ctx.stats.bytes_in += a.bytes_in; ctx.stats.bytes_out += a.bytes_out;
+    }
+
+    /* post: drop dependencies of everything that now has data (jit.cu:1484-1507) */
+    std::vector<uint32_t> side_effects;
+    for (auto &l : launches) {
+        for (uint32_t idx : l.first->sched) {
+            if (idx >= ctx.vars.size() || !ctx.vars[idx].used) continue;
+            EkVariable &v = ctx.vars[idx];
+            if (v.data != nullptr && v.op != EK_OP_INVALID && !v.direct_pointer) {
+                uint32_t deps[4] = { v.dep[0], v.dep[1], v.dep[2], v.dep[3] };
+                uint32_t extra = v.extra_dep;
+                v.dep[0] = v.dep[1] = v.dep[2] = v.dep[3] = 0; v.extra_dep = 0;
+                v.op = EK_OP_INVALID;
+                for (int k = 0; k < 4; ++k) if (deps[k] >= EK_REG_RESERVED) {
+                    /* dec_ref_int without re-entrancy surprises: var table may shrink but indices stay valid */
+                    EkVariable &d = ctx.vars[deps[k]];
+                    if (d.used && d.ref_int > 0) { if (--d.ref_int == 0 && d.ref_ext == 0) { d.ref_ext = 1; ek_dec_ref_ext(deps[k]); } }
+                }
+                if (extra >= EK_REG_RESERVED) ek_dec_ref_ext(extra);
+            }
+        }
+    }
+    for (auto &l : launches) {
+        for (uint32_t idx : l.first->sched) {
+            if (idx >= ctx.vars.size() || !ctx.vars[idx].used) continue;
+            EkVariable &v = ctx.vars[idx];
+            if (v.side_effect && v.op != EK_OP_INVALID) {
+                bool seen = std::find(side_effects.begin(), side_effects.end(), idx) != side_effects.end();
+                if (!seen) side_effects.push_back(idx);
+            }
+        }
+    }
+    for (uint32_t idx : side_effects) {
+        EkVariable &v = ctx.vars[idx];
+        v.side_effect = false;          /* executed; release the reference the trace held */
+        v.op = EK_OP_INVALID;
+        uint32_t deps[4] = { v.dep[0], v.dep[1], v.dep[2], v.dep[3] };
+        uint32_t extra = v.extra_dep;
+        v.dep[0] = v.dep[1] = v.dep[2] = v.dep[3] = 0; v.extra_dep = 0;
+        for (int k = 0; k < 4; ++k) if (deps[k] >= EK_REG_RESERVED) {
+            EkVariable &d = ctx.vars[deps[k]];
+            if (d.used && d.ref_int > 0) { if (--d.ref_int == 0 && d.ref_ext == 0) { d.ref_ext = 1; ek_dec_ref_ext(deps[k]); } }
+        }
+        if (extra >= EK_REG_RESERVED) ek_dec_ref_ext(extra);
+        ek_dec_ref_ext(idx);
+    }
+    return 0;
+}
+
+extern "C" {
+
+int ek_eval(void) { return eval_impl(false, nullptr); }
+
+int ek_eval_var(uint32_t index) {
+    EkContext &ctx = ek_ctx();
+    if (index < EK_REG_RESERVED || index >= ctx.vars.size() || !ctx.vars[index].used) {
+        ek_set_error("ek_eval_var(): unknown variable " + std::to_string(index));
+        return -1;
+    }
+    EkVariable &v = ctx.vars[index];
+    if (v.data == nullptr && v.op == EK_OP_LITERAL) {
+        /* literal: give it storage directly (no sweep needed) */
+        if (ek_init() != 0) return -1;
+        size_t es = ek_type_size(v.type);
+        void *p = ek_malloc(v.size * es);
+        ek_fill(p, es, v.imm, v.size);
+        ctx.vars[index].data = p; ctx.vars[index].free_data = true; ctx.vars[index].op = EK_OP_INVALID;
+        ctx.live.erase(index);
+        return 0;
+    }
+    if (v.data == nullptr || v.dirty) return ek_eval();          /* jit.cu:1510-1515 */
+    return 0;
+}
+
+/* host-only: assemble what ek_eval() would launch and return a textual listing (malloc'd).
+   Used by the CPU test-suite to check scheduling / register allocation without a GPU. */
+EK_API char *ek_debug_plan(void) {
+    std::string s;
+    if (eval_impl(true, &s) != 0) return nullptr;
+    return strdup(s.c_str());
+}
+
+} /* extern "C" */

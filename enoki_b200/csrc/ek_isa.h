@@ -1,0 +1,153 @@
+/*
+ * ek_isa.h -- device "sweep program" format shared by the host assembler
+ * (ek_runtime.cpp) and the fused sweep kernel (ek_sweep.cu).
+ *
+ * The reference lowers the expression DAG to a PTX string per launch
+ * (src/cuda/jit.cu:983-1227).  Here the DAG is lowered to a compact program of
+ * 16-byte instructions executed by ONE hand-written sm_100a kernel; every
+ * instruction processes V elements per thread with statically indexed registers,
+ * values that must outlive the next instruction live in a shared-memory slot
+ * file laid out [slot][group][thread] as 128-bit words.
+ */
+#pragma once
+#include <stdint.h>
+
+/* one instruction = 16 bytes */
+struct EkInstr {
+    uint16_t op;      /* EkDop */
+    uint16_t dst;     /* slot index for the result (if EKF_ST) / accumulator slot */
+    uint16_t a, b, c; /* operand codes */
+    uint16_t flags;
+    uint32_t imm;
+};
+
+/* operand codes */
+#define EK_OPND_NONE   0xFFFFu
+#define EK_OPND_ACC    0xFFFEu          /* result of the previous instruction (in registers) */
+#define EK_OPND_UNI    0x8000u          /* | word index into the uniform pool               */
+/* otherwise: slot index; indices >= n_tmp address the staged-input area of the
+   current pipeline stage                                                                   */
+
+/* flags */
+#define EKF_ST    0x0001u   /* store result to slot dst (dst+1 for the high plane)          */
+#define EKF_R64   0x0002u   /* result is 64 bit (two planes)                                */
+#define EKF_A64   0x0004u
+#define EKF_B64   0x0008u
+#define EKF_C64   0x0010u
+#define EKF_NARG(n) ((uint16_t)((n) << 8))
+#define EKF_GET_NARG(f) (((f) >> 8) & 3u)
+
+/* rounding modes for DOP_CVT_* (imm) */
+#define EK_RZ 0
+#define EK_RM 1
+#define EK_RP 2
+#define EK_RN 3
+
+/* reduction kinds */
+#define EK_RED_SUM 0
+#define EK_RED_PROD 1
+#define EK_RED_MIN 2
+#define EK_RED_MAX 3
+/* reduction value classes */
+#define EK_RC_F32 0
+#define EK_RC_I32 1
+#define EK_RC_U32 2
+#define EK_RC_F64 3
+#define EK_RC_I64 4
+#define EK_RC_U64 5
+
+#define EK_DOPS(X) \
+    X(NOP) X(END_SECTION) \
+    /* f32 */ \
+    X(ADD_F32) X(SUB_F32) X(MUL_F32) X(DIV_F32) X(FMA_F32) X(MIN_F32) X(MAX_F32) \
+    X(ABS_F32) X(NEG_F32) X(SQRT_F32) X(RCP_F32) X(RSQRT_F32) \
+    X(EXP_F32) X(LOG_F32) X(SIN_F32) X(COS_F32) \
+    X(FLOOR_F32) X(CEIL_F32) X(ROUND_F32) X(TRUNC_F32) X(MULNZ_F32) X(FMANZ_F32) \
+    X(LT_F32) X(LE_F32) X(GT_F32) X(GE_F32) X(EQ_F32) X(NE_F32) \
+    /* 32-bit integer */ \
+    X(ADD_I32) X(SUB_I32) X(MUL_I32) X(MULHI_I32) X(MULHI_U32) X(DIV_I32) X(DIV_U32) \
+    X(MOD_I32) X(MOD_U32) X(MAD_I32) X(MIN_I32) X(MIN_U32) X(MAX_I32) X(MAX_U32) \
+    X(ABS_I32) X(NEG_I32) X(SHL_32) X(SHR_I32) X(SHR_U32) X(NOT_32) X(AND_32) X(OR_32) X(XOR_32) \
+    X(POPC_32) X(CLZ_32) X(CTZ_32) \
+    X(LT_I32) X(LE_I32) X(GT_I32) X(GE_I32) X(LT_U32) X(LE_U32) X(GT_U32) X(GE_U32) X(EQ_32) X(NE_32) \
+    X(NOT_B) X(SEXT8) X(SEXT16) X(ZEXT8) X(ZEXT16) X(NEZ_32) \
+    /* f64 */ \
+    X(ADD_F64) X(SUB_F64) X(MUL_F64) X(DIV_F64) X(FMA_F64) X(MIN_F64) X(MAX_F64) \
+    X(ABS_F64) X(NEG_F64) X(SQRT_F64) X(RCP_F64) X(RSQRT_F64) \
+    X(EXP_F64) X(LOG_F64) X(SIN_F64) X(COS_F64) \
+    X(FLOOR_F64) X(CEIL_F64) X(ROUND_F64) X(TRUNC_F64) X(MULNZ_F64) X(FMANZ_F64) \
+    X(LT_F64) X(LE_F64) X(GT_F64) X(GE_F64) X(EQ_F64) X(NE_F64) \
+    /* 64-bit integer */ \
+    X(ADD_I64) X(SUB_I64) X(MUL_I64) X(MULHI_I64) X(MULHI_U64) X(DIV_I64) X(DIV_U64) \
+    X(MOD_I64) X(MOD_U64) X(MAD_I64) X(MIN_I64) X(MIN_U64) X(MAX_I64) X(MAX_U64) \
+    X(ABS_I64) X(NEG_I64) X(SHL_64) X(SHR_I64) X(SHR_U64) X(NOT_64) X(AND_64) X(OR_64) X(XOR_64) \
+    X(POPC_64) X(CLZ_64) X(CTZ_64) \
+    X(LT_I64) X(LE_I64) X(GT_I64) X(GE_I64) X(LT_U64) X(LE_U64) X(GT_U64) X(GE_U64) X(EQ_64) X(NE_64) \
+    /* select / move */ \
+    X(SELECT_32) X(SELECT_64) X(MOV_32) X(MOV_64) X(INDEX) \
+    /* conversions (imm = rounding mode for float->int) */ \
+    X(CVT_F32_I32) X(CVT_F32_U32) X(CVT_I32_F32) X(CVT_U32_F32) \
+    X(CVT_F32_F64) X(CVT_F64_F32) X(CVT_I32_F64) X(CVT_U32_F64) X(CVT_F64_I32) X(CVT_F64_U32) \
+    X(CVT_F32_I64) X(CVT_F32_U64) X(CVT_F64_I64) X(CVT_F64_U64) \
+    X(CVT_I64_F32) X(CVT_U64_F32) X(CVT_I64_F64) X(CVT_U64_F64) \
+    X(CVT_I32_I64) X(CVT_U32_U64) X(CVT_64_32) \
+    /* staged-input unpack (imm unused) */ \
+    X(LD_U8) X(LD_S8) X(LD_U16) X(LD_S16) X(LD_64) \
+    /* direct (non-staged) loads: imm = uniform index of base pointer */ \
+    X(LDG_32) X(LDG_64) X(LDG_U8) X(LDG_S8) X(LDG_U16) X(LDG_S16) \
+    /* stores: a = value, imm = uniform index of base pointer */ \
+    X(ST_32) X(ST_64) X(ST_8) X(ST_16) \
+    /* gathers: a = index, b = mask, imm = signed_index << 31 | stride << 16 | uniform index of base pointer */ \
+    X(GATHER_32) X(GATHER_64) X(GATHER_U8) X(GATHER_S8) X(GATHER_U16) X(GATHER_S16) X(GATHER_32_SMEM) \
+    /* scatters: a = index, b = value, c = mask; imm as for gathers */ \
+    X(SCATTER_32) X(SCATTER_64) X(SCATTER_8) X(SCATTER_16) \
+    X(SCATTER_ADD_F32) X(SCATTER_ADD_I32) X(SCATTER_ADD_F64) X(SCATTER_ADD_I64) \
+    X(SCATTER_ADD_F32_SMEM) X(SCATTER_ADD_I32_SMEM) \
+    /* reductions: body accumulate (a = value, dst = accumulator slot; imm = kind | class<<8), \
+       init (dst = accumulator slot), fini (a = accumulator slot, imm = kind|class<<8|red_index<<16) */ \
+    X(RACC) X(RINIT) X(RFIN) \
+    /* init/fini helpers for privatised scatter_add bins and staged gather tables \
+       (imm = descriptor index in the uniform pool) */ \
+    X(SMEM_ZERO) X(SMEM_LOAD_TABLE) X(SMEM_FLUSH_ADD_F32) X(SMEM_FLUSH_ADD_I32)
+
+enum EkDop : uint16_t {
+#define X(n) DOP_##n,
+    EK_DOPS(X)
+#undef X
+    DOP__COUNT
+};
+
+/* ---- launch arguments (passed by value as a __grid_constant__ kernel parameter) ---- */
+#define EK_MAX_STAGED   24      /* staged (TMA) input arrays per sweep                  */
+#define EK_MAX_ARGW     448     /* argument words appended to the uniform pool          */
+#define EK_MAX_SCALAR   64      /* size-1 evaluated inputs fetched in the prologue      */
+
+struct EkSweepArgs {
+    const EkInstr  *prog;          /* [n_init | n_body | n_fini] instructions (device memory) */
+    const uint32_t *lit;           /* literal words (device memory, cached with the program)  */
+    uint32_t n_init, n_body, n_fini;
+    uint32_t n_lit;                /* literal words -> uniform pool [0, n_lit)               */
+    uint32_t n_argw;               /* argument words -> uniform pool [n_lit, n_lit+n_argw)   */
+    uint32_t n_scalar;             /* scalar inputs -> uniform pool (2 words each) after args */
+    uint32_t n;                    /* number of elements                                      */
+    uint32_t n_tiles;              /* ceil(n / tile)                                          */
+    uint32_t n_tmp;                /* temporary slots                                         */
+    uint32_t n_in_units;           /* slot units per pipeline stage                           */
+    uint32_t n_staged;             /* staged input arrays                                     */
+    uint32_t n_stages;             /* pipeline depth (2..4)                                   */
+    uint32_t tma_ok;               /* all staged inputs 16-byte aligned                       */
+    uint32_t smem_bar_off;         /* byte offsets inside dynamic shared memory:              */
+    uint32_t smem_prog_off;        /*   mbarriers+reduction scratch, program copy,            */
+    uint32_t smem_extra_off;       /*   privatised bins / staged tables,                      */
+    uint32_t smem_slots_off;       /*   slot file (1024-byte aligned)                         */
+    uint32_t prog_in_smem;         /* copy the program to shared memory in the prologue       */
+    uint32_t n_red;                /* number of reductions                                    */
+    uint64_t *red_partials;        /* [n_red][grid] 8-byte partials                           */
+    uint32_t *red_counters;        /* [n_red] tickets (zero before and after the launch)      */
+    const void *staged_ptr[EK_MAX_STAGED];
+    uint16_t    staged_unit[EK_MAX_STAGED];   /* slot-unit offset inside a stage              */
+    uint8_t     staged_esize[EK_MAX_STAGED];  /* 1, 2, 4 or 8                                 */
+    const void *scalar_ptr[EK_MAX_SCALAR];
+    uint8_t     scalar_type[EK_MAX_SCALAR];   /* ek_type                                      */
+    uint32_t    argw[EK_MAX_ARGW];
+};

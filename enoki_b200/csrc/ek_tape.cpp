@@ -1,0 +1,910 @@
+/*
+ * ek_tape.cpp -- reverse/forward-mode tape runtime.
+ *
+ * Behavioural spec = src/autodiff/autodiff.cpp of the reference:
+ *   Node/Edge/Special/Detail :44-192, append* :266-338, special edges :354-608,
+ *   append_edge :610-643, ref counting :681-774, set_gradient :822-836,
+ *   backward :838-910, forward :912-988, safe_mul/safe_fmadd :1191-1221.
+ *
+ * Re-designed for the GPU: instead of growing the evaluator trace by four nodes
+ * per edge (the reference's CUDA branch), backward() levels the reachable sub-graph
+ * and runs ONE adjoint kernel per level over materialised weights (ek_adjoint.cu).
+ * Sources that need something the kernel does not do (special edges, size-1 sources
+ * of wide edges -> hsum, pre-seeded gradients) take a generic path that records the
+ * reference's exact op sequence through the evaluator (MUL_NZ / FMA_NZ / HSUM ...).
+ * Per source, contributions are accumulated in descending target id -- the
+ * reference's order -- so fp results match the CPU tape bit for bit.
+ */
+#include "ek_internal.h"
+#include "ek_adjoint.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <sstream>
+#include <unordered_set>
+
+namespace {
+
+enum SpecialKind { SP_GATHER, SP_SCATTER, SP_PSUM, SP_REVERSE };
+
+struct Special {
+    SpecialKind kind;
+    uint32_t offset = 0, mask = 0;      /* evaluator variables (one ext ref each) */
+    size_t size = 0;
+    bool permute = false, scatter_add = false;
+    ~Special() { if (offset) ek_dec_ref_ext(offset); if (mask) ek_dec_ref_ext(mask); }
+};
+
+struct TEdge {
+    uint32_t source = 0;
+    uint32_t weight = 0;                 /* evaluator variable (one ext ref) */
+    Special *special = nullptr;
+};
+
+struct TNode {
+    std::string label;
+    uint32_t grad = 0;                   /* evaluator variable (one ext ref), 0 = empty */
+    std::vector<TEdge> edges;            /* in-edges */
+    std::vector<uint32_t> edges_rev;     /* targets of out-edges */
+    uint32_t ref_ext = 0, ref_int = 0;
+    uint32_t size = 0;
+};
+
+struct Tape {
+    ek_type vt = EK_FLOAT32;
+    std::unordered_map<uint32_t, TNode> nodes;
+    uint32_t node_counter = 1, node_counter_last = 1;
+    std::vector<std::string> prefix;
+    uint32_t *sg_index = nullptr;
+    size_t sg_size = 0;
+    bool sg_permute = false;
+    uint32_t log_level = 0;
+    bool graph_simplification = true, is_simplified = true;
+    std::set<uint32_t> scheduled;
+    /* staging for adjoint descriptors (persistent, grown on demand) */
+    void *h_stage = nullptr, *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t stage_done = nullptr;
+};
+
+Tape *g_tapes[2] = { nullptr, nullptr };
+
+Tape *tape_of(ek_type t) {
+    int i = t == EK_FLOAT64 ? 1 : 0;
+    if (t != EK_FLOAT32 && t != EK_FLOAT64) { ek_set_error("tape: value type must be Float32 or Float64"); return nullptr; }
+    if (!g_tapes[i]) { g_tapes[i] = new Tape(); g_tapes[i]->vt = t; }
+    return g_tapes[i];
+}
+
+TNode *node(Tape &T, uint32_t idx) {
+    auto it = T.nodes.find(idx);
+    if (it == T.nodes.end()) { ek_set_error("autodiff: Detail::node(): Unknown index " + std::to_string(idx)); return nullptr; }   /* autodiff.cpp:164-169 */
+    return &it->second;
+}
+
+/* ---- evaluator helpers ---- */
+uint32_t v_literal(ek_type t, double value) {
+    uint64_t bits;
+    if (t == EK_FLOAT32) { float f = (float) value; uint32_t u; memcpy(&u, &f, 4); bits = u; }
+    else memcpy(&bits, &value, 8);
+    return ek_trace_append(t, EK_OP_LITERAL, 0, 0, 0, bits);
+}
+uint32_t v_op(ek_type t, ek_op op, uint32_t a, uint32_t b = 0, uint32_t c = 0, uint64_t imm = 0) {
+    return ek_trace_append(t, op, a, b, c, imm);
+}
+void set_grad(TNode &n, uint32_t h /* takes ownership of one ext ref */) {
+    if (n.grad) ek_dec_ref_ext(n.grad);
+    n.grad = h;
+}
+
+void free_node(Tape &T, uint32_t idx);
+
+void inc_ref_int(Tape &T, uint32_t idx, uint32_t from) {
+    TNode *n = node(T, idx); if (!n) return;
+    n->edges_rev.push_back(from);
+    n->ref_int++;
+}
+void dec_ref_int(Tape &T, uint32_t idx, uint32_t from) {
+    if (idx == 0) return;
+    TNode *n = node(T, idx); if (!n) return;
+    if (n->ref_int == 0) { fprintf(stderr, "autodiff: dec_ref_int(): Node %u has no internal references!\n", idx); exit(EXIT_FAILURE); }
+    --n->ref_int;
+    auto it = std::find(n->edges_rev.begin(), n->edges_rev.end(), from);
+    if (it != n->edges_rev.end()) n->edges_rev.erase(it);
+    if (n->ref_int == 0 && n->ref_ext == 0) free_node(T, idx);
+}
+void inc_ref_ext(Tape &T, uint32_t idx) {
+    if (idx == 0) return;
+    TNode *n = node(T, idx); if (n) n->ref_ext++;
+}
+void dec_ref_ext(Tape &T, uint32_t idx) {
+    if (idx == 0) return;
+    auto it = T.nodes.find(idx);
+    if (it == T.nodes.end()) return;
+    TNode &n = it->second;
+    if (n.ref_ext == 0) { fprintf(stderr, "autodiff: dec_ref_ext(): Node %u has no external references!\n", idx); exit(EXIT_FAILURE); }
+    --n.ref_ext;
+    if (n.ref_int == 0 && n.ref_ext == 0) free_node(T, idx);
+}
+void release_edge(TEdge &e) {
+    if (e.weight) { ek_dec_ref_ext(e.weight); e.weight = 0; }
+    delete e.special; e.special = nullptr;
+}
+/* autodiff.cpp:759-774, iterative */
+void free_node(Tape &T, uint32_t first) {
+    std::vector<uint32_t> work { first };
+    while (!work.empty()) {
+        uint32_t idx = work.back(); work.pop_back();
+        auto it = T.nodes.find(idx);
+        if (it == T.nodes.end()) continue;
+        TNode &n = it->second;
+        if (n.ref_int != 0 || n.ref_ext != 0) continue;
+        for (TEdge &e : n.edges) {
+            if (e.source) {
+                auto sit = T.nodes.find(e.source);
+                if (sit != T.nodes.end()) {
+                    TNode &s = sit->second;
+                    if (s.ref_int > 0) --s.ref_int;
+                    auto r = std::find(s.edges_rev.begin(), s.edges_rev.end(), idx);
+                    if (r != s.edges_rev.end()) s.edges_rev.erase(r);
+                    if (s.ref_int == 0 && s.ref_ext == 0) work.push_back(e.source);
+                }
+            }
+            release_edge(e);
+        }
+        if (n.grad) ek_dec_ref_ext(n.grad);
+        T.nodes.erase(it);
+    }
+}
+
+uint32_t append_node(Tape &T, size_t size, const char *label) {
+    uint32_t idx = T.node_counter++;
+    TNode &n = T.nodes[idx];
+    n.size = (uint32_t) size;
+    n.label = label ? label : "";
+    for (auto it = T.prefix.rbegin(); it != T.prefix.rend(); ++it) n.label = *it + '/' + n.label;
+    n.ref_ext = 1;
+    T.is_simplified = false;
+    return idx;
+}
+
+int append_edge(Tape &T, uint32_t src, uint32_t dst, uint32_t weight) {
+    if (src == 0) return 0;
+    TNode *t = node(T, dst); if (!t) return -1;
+    if (!node(T, src)) return -1;
+    for (TEdge &e : t->edges) {
+        if (e.source == src && !e.special) {           /* merge duplicate edges: autodiff.cpp:624-633 */
+            uint32_t sum = v_op(T.vt, EK_OP_ADD, e.weight, weight);
+            if (!sum) return -1;
+            ek_dec_ref_ext(e.weight);
+            e.weight = sum;
+            return 0;
+        }
+    }
+    TEdge e; e.source = src; e.weight = weight;
+    ek_inc_ref_ext(weight);
+    t->edges.push_back(e);
+    inc_ref_int(T, src, dst);
+    return 0;
+}
+
+void dfs(Tape &T, uint32_t root, bool backward, bool clear_grad) {
+    /* autodiff.cpp:171-191, iterative */
+    std::vector<uint32_t> stack { root };
+    while (!stack.empty()) {
+        uint32_t k = stack.back(); stack.pop_back();
+        if (T.scheduled.count(k)) continue;
+        TNode *n = node(T, k); if (!n) continue;
+        T.scheduled.insert(k);
+        if (clear_grad) set_grad(*n, 0);
+        if (backward) { for (const TEdge &e : n->edges) if (e.source) stack.push_back(e.source); }
+        else { for (uint32_t k2 : n->edges_rev) stack.push_back(k2); }
+    }
+}
+
+/* broadcast a size-1 gradient to the node size (autodiff.cpp:851-861) */
+int fix_grad_size(Tape &T, TNode &n) {
+    if (!n.grad) return 0;
+    size_t gs = ek_var_size(n.grad);
+    if (gs == n.size) return 0;
+    if (gs == 1) {
+        uint32_t h = ek_var_set_size(n.grad, n.size, 1);
+        if (!h) return -1;
+        n.grad = h;
+        return 0;
+    }
+    ek_set_error("backward(): gradient sizes don't match: expected " + std::to_string(n.size) + ", got " + std::to_string(gs));
+    return -1;
+}
+
+/* literal value of a size-1 variable if it can be determined without evaluating it */
+bool var_imm(uint32_t h, uint64_t &bits) {
+    EkContext &ctx = ek_ctx();
+    const EkVariable *v = &ctx.vars[h];
+    if (v->op == EK_OP_MOV && v->data == nullptr && v->dep[0] >= EK_REG_RESERVED) v = &ctx.vars[v->dep[0]];   /* set_slices of a literal */
+    if (v->op == EK_OP_LITERAL && v->data == nullptr) { bits = v->imm; return true; }
+    return false;
+}
+
+/* ---- generic (trace-recorded) accumulation of one source, autodiff.cpp:863-888 + specials ---- */
+int accumulate_generic(Tape &T, uint32_t sidx, TNode &s, const std::vector<std::pair<uint32_t, TEdge *>> &out) {
+    for (auto &te : out) {
+        TNode &t = *node(T, te.first);
+        TEdge &e = *te.second;
+        if (fix_grad_size(T, t) != 0) return -1;
+        uint32_t g = t.grad;
+        if (!g) continue;
+        if (!e.special) {
+            size_t ws = ek_var_size(e.weight), gs = ek_var_size(g);
+            if (s.size == 1 && (ws != 1 || gs != 1)) {
+                uint32_t m = v_op(T.vt, EK_OP_MUL_NZ, e.weight, g); if (!m) return -1;
+                uint32_t h = v_op(T.vt, EK_OP_HSUM, m); ek_dec_ref_ext(m); if (!h) return -1;
+                if (!s.grad) set_grad(s, h);
+                else { uint32_t a = v_op(T.vt, EK_OP_ADD, s.grad, h); ek_dec_ref_ext(h); if (!a) return -1; set_grad(s, a); }
+            } else {
+                uint32_t r = s.grad ? v_op(T.vt, EK_OP_FMA_NZ, e.weight, g, s.grad) : v_op(T.vt, EK_OP_MUL_NZ, e.weight, g);
+                if (!r) return -1;
+                set_grad(s, r);
+            }
+            ek_ctx().stats.edge_adjoints += std::max<uint64_t>(std::max<uint64_t>(ws, gs), s.size);
+        } else {
+            const Special &sp = *e.special;
+            switch (sp.kind) {
+                case SP_GATHER: {              /* autodiff.cpp:384-398: scatter(_add) into a zero-initialised source grad */
+                    size_t es = ek_type_size(T.vt);
+                    if (!s.grad) {
+                        void *p = ek_malloc(sp.size * es);
+                        ek_fill(p, 1, 0, sp.size * es);
+                        set_grad(s, ek_var_register(T.vt, sp.size, p, 1));
+                    } else if (ek_var_size(s.grad) != sp.size) { ek_set_error("Internal error in Gather::backward()!"); return -1; }
+                    if (ek_eval_var(s.grad) != 0) return -1;
+                    if (ek_set_scatter_gather_operand(s.grad, 0) != 0) return -1;
+                    uint32_t ptr = ek_var_register_ptr(ek_var_ptr(s.grad));
+                    uint32_t h = v_op(sp.permute ? EK_UINT64 : T.vt, sp.permute ? EK_OP_SCATTER : EK_OP_SCATTER_ADD, ptr, sp.offset, sp.mask,
+                                      ((uint64_t) es << 32) | g);
+                    ek_dec_ref_ext(ptr);
+                    ek_set_scatter_gather_operand(0, 0);
+                    if (!h) return -1;
+                    ek_var_mark_side_effect(h);
+                    ek_var_mark_dirty(s.grad);
+                } break;
+                case SP_SCATTER: {             /* autodiff.cpp:553-571: gather (+ hsum for size-1 sources) */
+                    if (ek_var_size(g) != sp.size) { ek_set_error("Internal error in Scatter::backward()!"); return -1; }
+                    if (ek_set_scatter_gather_operand(g, 1) != 0) return -1;
+                    uint32_t ptr = ek_var_register_ptr(ek_var_ptr(g));
+                    uint32_t r = v_op(T.vt, EK_OP_GATHER, ptr, sp.offset, sp.mask, ek_type_size(T.vt));
+                    ek_dec_ref_ext(ptr);
+                    ek_set_scatter_gather_operand(0, 0);
+                    if (!r) return -1;
+                    if (s.size == 1 && ek_var_size(r) != 1) { uint32_t h = v_op(T.vt, EK_OP_HSUM, r); ek_dec_ref_ext(r); r = h; if (!r) return -1; }
+                    else if (ek_var_size(r) == 1 && s.size != 1) { r = ek_var_set_size(r, s.size, 1); if (!r) return -1; }
+                    if (!s.grad) set_grad(s, r);
+                    else { uint32_t a = v_op(T.vt, EK_OP_ADD, s.grad, r); ek_dec_ref_ext(r); if (!a) return -1; set_grad(s, a); }
+                } break;
+                case SP_REVERSE: {             /* autodiff.cpp:442-452 */
+                    if (ek_eval_var(g) != 0) return -1;
+                    size_t n = ek_var_size(g), es = ek_type_size(T.vt);
+                    void *p = ek_malloc(n * es);
+                    ek_reverse(p, ek_var_ptr(g), es, n);
+                    uint32_t r = ek_var_register(T.vt, n, p, 1);
+                    if (!s.grad) set_grad(s, r);
+                    else { uint32_t a = v_op(T.vt, EK_OP_ADD, s.grad, r); ek_dec_ref_ext(r); if (!a) return -1; set_grad(s, a); }
+                } break;
+                case SP_PSUM: {                /* autodiff.cpp:492-502: reverse(psum(reverse(g))) */
+                    if (ek_eval_var(g) != 0) return -1;
+                    size_t n = ek_var_size(g), es = ek_type_size(T.vt);
+                    void *r1 = ek_malloc(n * es);
+                    ek_reverse(r1, ek_var_ptr(g), es, n);
+                    void *ps = ek_psum(T.vt, n, r1);
+                    if (!ps) { ek_free(r1); return -1; }
+                    ek_reverse(r1, ps, es, n);
+                    ek_free(ps);
+                    uint32_t r = ek_var_register(T.vt, n, r1, 1);
+                    if (!s.grad) set_grad(s, r);
+                    else { uint32_t a = v_op(T.vt, EK_OP_ADD, s.grad, r); ek_dec_ref_ext(r); if (!a) return -1; set_grad(s, a); }
+                } break;
+            }
+        }
+    }
+    (void) sidx;
+    return 0;
+}
+
+/* end-of-target bookkeeping, autodiff.cpp:884-898 */
+void finalize_target(Tape &T, uint32_t tidx, bool free_graph) {
+    auto it = T.nodes.find(tidx);
+    if (it == T.nodes.end()) return;
+    TNode &t = it->second;
+    if (free_graph) {
+        if (!t.edges.empty()) {
+            std::vector<TEdge> edges;
+            edges.swap(t.edges);
+            set_grad(t, 0);
+            for (TEdge &e : edges) { uint32_t src = e.source; release_edge(e); dec_ref_int(T, src, tidx); }
+        }
+        dec_ref_ext(T, tidx);
+    } else {
+        if (t.ref_int > 0) set_grad(t, 0);
+    }
+}
+
+int backward_impl(Tape &T, bool free_graph) {
+    EkContext &ctx = ek_ctx();
+    std::vector<uint32_t> sched(T.scheduled.begin(), T.scheduled.end());     /* ascending */
+    if (sched.empty()) return 0;
+    if (ek_init() != 0) return -1;
+    if (free_graph) for (uint32_t idx : sched) inc_ref_ext(T, idx);
+    const size_t es = ek_type_size(T.vt);
+
+    /* ---- levels: longest distance from a root over out-edges ---- */
+    std::unordered_map<uint32_t, uint32_t> pos;
+    pos.reserve(sched.size() * 2);
+    for (size_t i = 0; i < sched.size(); ++i) pos[sched[i]] = (uint32_t) i;
+    std::vector<uint32_t> level(sched.size(), 0), remaining(sched.size(), 0);
+    uint32_t max_level = 0;
+    bool need_eval = false;
+    size_t total_terms = 0;
+    for (size_t i = sched.size(); i-- > 0;) {
+        TNode &t = *node(T, sched[i]);
+        remaining[i] = (uint32_t) t.edges.size();
+        for (const TEdge &e : t.edges) {
+            auto p = pos.find(e.source);
+            if (p == pos.end()) continue;
+            level[p->second] = std::max(level[p->second], level[i] + 1);
+            max_level = std::max(max_level, level[p->second]);
+            ++total_terms;
+            if (!e.special) {
+                const EkVariable &w = ctx.vars[e.weight];
+                uint64_t bits;
+                if (w.data == nullptr && !var_imm(e.weight, bits)) need_eval = true;
+            }
+        }
+    }
+    if (need_eval && ek_eval() != 0) return -1;           /* materialise all edge weights at once */
+
+    std::vector<std::vector<uint32_t>> by_level(max_level + 1);
+    for (size_t i = 0; i < sched.size(); ++i) by_level[level[i]].push_back((uint32_t) i);
+
+    /* ---- descriptor staging: [jobs | terms | chunk_start] per level, one H2D copy each ---- */
+    size_t need = sched.size() * (sizeof(EkAdjJob) + 4) + total_terms * sizeof(EkAdjTerm) + 64 * (max_level + 2);
+    if (need > T.stage_bytes) {
+        if (T.stage_done) { ek_cuda_check(cudaEventSynchronize(T.stage_done)); }
+        if (T.h_stage) ek_host_free(T.h_stage);
+        if (T.d_stage) ek_free(T.d_stage);
+        T.stage_bytes = need + need / 2;
+        T.h_stage = ek_host_malloc(T.stage_bytes);
+        T.d_stage = ek_malloc(T.stage_bytes);
+    }
+    if (!T.stage_done) ek_cuda_check(cudaEventCreateWithFlags(&T.stage_done, cudaEventDisableTiming));
+    else ek_cuda_check(cudaEventSynchronize(T.stage_done));   /* previous backward() has consumed the staging area */
+    size_t stage_off = 0;
+
+    auto finalize_if_done = [&](uint32_t p) {
+        if (remaining[p] == 0) finalize_target(T, sched[p], free_graph);
+    };
+
+    /* roots / level 0: nothing to accumulate; leaves among them are finalised at once */
+    for (uint32_t p : by_level[0]) {
+        TNode &t = *node(T, sched[p]);
+        if (t.edges.empty()) finalize_target(T, sched[p], free_graph);
+    }
+
+    std::vector<std::pair<uint32_t, TEdge *>> out;
+    std::vector<EkAdjJob> jobs;
+    std::vector<EkAdjTerm> terms;
+    std::vector<uint32_t> chunk_start;
+    std::vector<uint32_t> job_pos;
+
+    for (uint32_t L = 1; L <= max_level; ++L) {
+        jobs.clear(); terms.clear(); chunk_start.clear(); job_pos.clear();
+        uint32_t n_chunks = 0;
+        std::vector<uint32_t> generic;
+        bool level_needs_eval = false;
+
+        /* pass 1: which target gradients of this level are still unevaluated traces? */
+        for (uint32_t p : by_level[L]) {
+            TNode &s = *node(T, sched[p]);
+            for (uint32_t tid : s.edges_rev) {
+                auto tp = pos.find(tid); if (tp == pos.end()) continue;
+                TNode &t = *node(T, tid);
+                if (!t.grad) continue;
+                uint64_t bits;
+                if (ctx.vars[t.grad].data == nullptr && !var_imm(t.grad, bits)) level_needs_eval = true;
+            }
+        }
+        if (level_needs_eval && ek_eval() != 0) return -1;
+
+        for (uint32_t p : by_level[L]) {
+            uint32_t sidx = sched[p];
+            TNode &s = *node(T, sidx);
+            out.clear();
+            for (uint32_t tid : s.edges_rev) {
+                if (!pos.count(tid)) continue;
+                TNode &t = *node(T, tid);
+                for (TEdge &e : t.edges) if (e.source == sidx) out.emplace_back(tid, &e);
+            }
+            std::sort(out.begin(), out.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+
+            bool simple = s.grad == 0;
+            for (auto &te : out) {
+                TNode &t = *node(T, te.first);
+                if (te.second->special) { simple = false; break; }
+                size_t ws = ek_var_size(te.second->weight);
+                size_t gs = t.grad ? ek_var_size(t.grad) : 1;
+                if (s.size == 1 && (ws != 1 || gs != 1)) { simple = false; break; }
+                if ((ws != 1 && ws != s.size) || (gs != 1 && gs != s.size)) { simple = false; break; }
+            }
+            if (!simple) { generic.push_back(p); continue; }
+
+            EkAdjJob job;
+            job.first_term = (uint32_t) terms.size(); job.n_terms = 0; job.size = s.size; job.aligned = 1;
+            for (auto &te : out) {
+                TNode &t = *node(T, te.first);
+                if (!t.grad) continue;                      /* empty adjoint contributes nothing */
+                EkAdjTerm term; term.pad = 0;
+                uint32_t wk, gk; uint64_t bits;
+                const EkVariable &w = ctx.vars[te.second->weight];
+                if (w.data != nullptr) { wk = w.size == 1 ? EK_ADJ_SCALAR : EK_ADJ_ARRAY; term.w = (uint64_t) (uintptr_t) w.data; }
+                else if (var_imm(te.second->weight, bits)) { wk = EK_ADJ_IMM; term.w = bits; }
+                else { ek_set_error("backward(): internal error: edge weight not materialised"); return -1; }
+                const EkVariable &g = ctx.vars[t.grad];
+                if (g.data != nullptr) { gk = g.size == 1 ? EK_ADJ_SCALAR : EK_ADJ_ARRAY; term.g = (uint64_t) (uintptr_t) g.data; }
+                else if (var_imm(t.grad, bits)) { gk = EK_ADJ_IMM; term.g = bits; }
+                else { ek_set_error("backward(): internal error: target adjoint not materialised"); return -1; }
+                if ((wk == EK_ADJ_ARRAY && (term.w & 15u)) || (gk == EK_ADJ_ARRAY && (term.g & 15u))) job.aligned = 0;
+                term.flags = wk | (gk << 2);
+                terms.push_back(term);
+                job.n_terms++;
+                ctx.stats.edge_adjoints += s.size;
+            }
+            if (job.n_terms > 0) {
+                void *dst = ek_malloc((size_t) s.size * es);
+                job.dst = (uint64_t) (uintptr_t) dst;
+                set_grad(s, ek_var_register(T.vt, s.size, dst, 1));
+                chunk_start.push_back(n_chunks);
+                n_chunks += (s.size + EK_ADJ_CHUNK - 1) / EK_ADJ_CHUNK;
+                jobs.push_back(job);
+            } else {
+                terms.resize(job.first_term);
+            }
+            job_pos.push_back(p);
+        }
+
+        if (!jobs.empty()) {
+            size_t jb = jobs.size() * sizeof(EkAdjJob), tb = terms.size() * sizeof(EkAdjTerm), cb = chunk_start.size() * 4;
+            size_t o_jobs = stage_off, o_terms = (o_jobs + jb + 15) & ~(size_t) 15, o_chunks = (o_terms + tb + 15) & ~(size_t) 15;
+            size_t end = (o_chunks + cb + 15) & ~(size_t) 15;
+            if (end > T.stage_bytes) { ek_set_error("backward(): internal error: staging overflow"); return -1; }
+            uint8_t *h = (uint8_t *) T.h_stage, *d = (uint8_t *) T.d_stage;
+            memcpy(h + o_jobs, jobs.data(), jb); memcpy(h + o_terms, terms.data(), tb); memcpy(h + o_chunks, chunk_start.data(), cb);
+            ek_cuda_check(cudaMemcpyAsync(d + o_jobs, h + o_jobs, end - o_jobs, cudaMemcpyHostToDevice, ctx.stream));
+            unsigned grid = std::min<uint32_t>(n_chunks, (uint32_t) ctx.num_sms * 8u);
+            if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
+            ek_cuda_check(ek_launch_adjoint(T.vt == EK_FLOAT64, (const EkAdjJob *) (d + o_jobs), (const EkAdjTerm *) (d + o_terms),
+                                            (const uint32_t *) (d + o_chunks), (uint32_t) jobs.size(), n_chunks, grid, ctx.stream));
+            if (ctx.timing) {
+                ek_cuda_check(cudaEventRecord(ctx.ev_stop, ctx.stream));
+                ek_cuda_check(cudaEventSynchronize(ctx.ev_stop));
+                float ms = 0; ek_cuda_check(cudaEventElapsedTime(&ms, ctx.ev_start, ctx.ev_stop));
+                ctx.stats.last_kernel_ms = ms; ctx.stats.total_kernel_ms += ms;
+            }
+            ctx.stats.launches++; ctx.stats.adjoint_launches++;
+            stage_off = end;
+        }
+
+        /* generic sources of this level (special edges, hsum into scalars, pre-seeded grads) */
+        for (uint32_t p : generic) {
+            uint32_t sidx = sched[p];
+            TNode &s = *node(T, sidx);
+            out.clear();
+            for (uint32_t tid : s.edges_rev) {
+                if (!pos.count(tid)) continue;
+                TNode &t = *node(T, tid);
+                for (TEdge &e : t.edges) if (e.source == sidx) out.emplace_back(tid, &e);
+            }
+            std::sort(out.begin(), out.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+            if (accumulate_generic(T, sidx, s, out) != 0) return -1;
+            job_pos.push_back(p);
+        }
+
+        /* bookkeeping: every processed source has consumed one in-edge of each of its targets */
+        for (uint32_t p : job_pos) {
+            uint32_t sidx = sched[p];
+            std::vector<uint32_t> targets;
+            {
+                TNode &s = *node(T, sidx);
+                for (uint32_t tid : s.edges_rev) if (pos.count(tid)) targets.push_back(tid);
+            }
+            for (uint32_t tid : targets) {
+                uint32_t tp = pos[tid];
+                auto it = T.nodes.find(tid);
+                if (it == T.nodes.end()) continue;
+                uint32_t cnt = 0;
+                for (const TEdge &e : it->second.edges) if (e.source == sidx) ++cnt;
+                remaining[tp] -= std::min(remaining[tp], cnt);
+                finalize_if_done(tp);
+            }
+            /* a source without in-edges (leaf) is complete now */
+            auto sit = T.nodes.find(sidx);
+            if (sit != T.nodes.end() && sit->second.edges.empty()) finalize_target(T, sidx, free_graph);
+        }
+    }
+    ek_cuda_check(cudaEventRecord(T.stage_done, ctx.stream));
+
+    if (T.log_level >= 1)
+        fprintf(stderr, "autodiff: backward(): processed %zu/%u nodes.\n", sched.size(), T.node_counter - T.node_counter_last);
+    if (free_graph) T.node_counter_last = T.node_counter;
+    T.scheduled.clear();
+    return 0;
+}
+
+/* forward mode, autodiff.cpp:912-988 (recorded through the evaluator) */
+int forward_impl(Tape &T, bool free_graph) {
+    std::vector<uint32_t> sched(T.scheduled.begin(), T.scheduled.end());
+    if (free_graph) for (uint32_t idx : sched) inc_ref_ext(T, idx);
+    for (uint32_t sidx : sched) {
+        auto sit = T.nodes.find(sidx);
+        if (sit == T.nodes.end()) continue;
+        TNode &s = sit->second;
+        if (s.size == 1 && s.grad && ek_var_size(s.grad) > 1) {
+            uint32_t h = v_op(T.vt, EK_OP_HSUM, s.grad); if (!h) return -1; set_grad(s, h);
+        }
+        std::vector<uint32_t> targets = s.edges_rev;
+        for (uint32_t tidx : targets) {
+            TNode *tp = node(T, tidx); if (!tp) return -1;
+            TNode &t = *tp;
+            TEdge *e = nullptr;
+            for (TEdge &x : t.edges) if (x.source == sidx) { e = &x; break; }
+            if (!e) { ek_set_error("forward(): invalid graph structure!"); return -1; }
+            if (s.grad) {
+                if (!e->special) {
+                    size_t ws = ek_var_size(e->weight), gs = ek_var_size(s.grad);
+                    if (t.size == 1 && (ws != 1 || gs != 1)) {
+                        uint32_t m = v_op(T.vt, EK_OP_MUL_NZ, e->weight, s.grad); if (!m) return -1;
+                        uint32_t h = v_op(T.vt, EK_OP_HSUM, m); ek_dec_ref_ext(m); if (!h) return -1;
+                        if (!t.grad) set_grad(t, h);
+                        else { uint32_t a = v_op(T.vt, EK_OP_ADD, t.grad, h); ek_dec_ref_ext(h); if (!a) return -1; set_grad(t, a); }
+                    } else {
+                        uint32_t r = t.grad ? v_op(T.vt, EK_OP_FMA_NZ, e->weight, s.grad, t.grad) : v_op(T.vt, EK_OP_MUL_NZ, e->weight, s.grad);
+                        if (!r) return -1;
+                        set_grad(t, r);
+                    }
+                } else {
+                    const Special &sp = *e->special;
+                    uint32_t g = s.grad;
+                    switch (sp.kind) {
+                        case SP_GATHER: {          /* autodiff.cpp:367-382 */
+                            if (ek_var_size(g) != sp.size) { ek_set_error("Internal error in Gather::forward()!"); return -1; }
+                            if (ek_set_scatter_gather_operand(g, 1) != 0) return -1;
+                            uint32_t ptr = ek_var_register_ptr(ek_var_ptr(g));
+                            uint32_t r = v_op(T.vt, EK_OP_GATHER, ptr, sp.offset, sp.mask, ek_type_size(T.vt));
+                            ek_dec_ref_ext(ptr);
+                            ek_set_scatter_gather_operand(0, 0);
+                            if (!r) return -1;
+                            if (!t.grad) set_grad(t, r);
+                            else { uint32_t a = v_op(T.vt, EK_OP_ADD, t.grad, r); ek_dec_ref_ext(r); if (!a) return -1; set_grad(t, a); }
+                        } break;
+                        case SP_SCATTER: {         /* autodiff.cpp:536-551 */
+                            size_t es = ek_type_size(T.vt);
+                            if (!t.grad) {
+                                void *p = ek_malloc(sp.size * es);
+                                ek_fill(p, 1, 0, sp.size * es);
+                                set_grad(t, ek_var_register(T.vt, sp.size, p, 1));
+                            } else if (ek_var_size(t.grad) != sp.size) { ek_set_error("Internal error in Scatter::forward()!"); return -1; }
+                            if (ek_eval_var(t.grad) != 0) return -1;
+                            if (ek_set_scatter_gather_operand(t.grad, 0) != 0) return -1;
+                            uint32_t ptr = ek_var_register_ptr(ek_var_ptr(t.grad));
+                            uint32_t h = v_op(sp.scatter_add ? T.vt : EK_UINT64, sp.scatter_add ? EK_OP_SCATTER_ADD : EK_OP_SCATTER, ptr, sp.offset, sp.mask,
+                                              ((uint64_t) es << 32) | g);
+                            ek_dec_ref_ext(ptr);
+                            ek_set_scatter_gather_operand(0, 0);
+                            if (!h) return -1;
+                            ek_var_mark_side_effect(h);
+                            ek_var_mark_dirty(t.grad);
+                        } break;
+                        default:
+                            ek_set_error("forward(): psum/reverse edges are not implemented yet");
+                            return -1;
+                    }
+                }
+            }
+            if (fix_grad_size(T, t) != 0) return -1;
+        }
+        if (s.ref_int > 0) set_grad(s, 0);
+        if (free_graph) {
+            std::vector<uint32_t> rev = s.edges_rev;
+            for (uint32_t tidx : rev) {
+                TNode *tp = node(T, tidx); if (!tp) continue;
+                for (auto it = tp->edges.begin(); it != tp->edges.end(); ++it)
+                    if (it->source == sidx) { release_edge(*it); tp->edges.erase(it); break; }
+                dec_ref_int(T, sidx, tidx);
+            }
+            dec_ref_ext(T, sidx);
+        }
+    }
+    if (free_graph) T.node_counter_last = T.node_counter;
+    T.scheduled.clear();
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+uint32_t ek_tape_append_node(ek_type t, size_t size, const char *label) {
+    Tape *T = tape_of(t); if (!T) return 0;
+    return append_node(*T, size, label);
+}
+
+uint32_t ek_tape_append_leaf(ek_type t, size_t size) {
+    Tape *T = tape_of(t); if (!T) return 0;
+    uint32_t idx = append_node(*T, size, "'unnamed'");
+    /* autodiff.cpp:331-338: leaf gets a zero gradient */
+    TNode &n = T->nodes[idx];
+    uint32_t z = v_literal(t, 0.0);
+    if (size != 1) z = ek_var_set_size(z, size, 1);
+    set_grad(n, z);
+    return idx;
+}
+
+int ek_tape_append_edge(ek_type t, uint32_t src, uint32_t dst, uint32_t weight) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    return append_edge(*T, src, dst, weight);
+}
+
+uint32_t ek_tape_append(ek_type t, const char *label, size_t size, uint32_t n_in,
+                        const uint32_t *in, const uint32_t *weights) {
+    Tape *T = tape_of(t); if (!T) return 0;
+    bool any = false;
+    for (uint32_t i = 0; i < n_in; ++i) any |= in[i] != 0;
+    if (!any) return 0;                                   /* autodiff.cpp:268-269 */
+    uint32_t idx = append_node(*T, size, label);
+    for (uint32_t i = 0; i < n_in; ++i)
+        if (append_edge(*T, in[i], idx, weights[i]) != 0) return 0;
+    return idx;
+}
+
+uint32_t ek_tape_append_gather(ek_type t, uint32_t offset_var, uint32_t mask_var) {
+    Tape *T = tape_of(t); if (!T) return 0;
+    if (T->sg_index == nullptr || *T->sg_index == 0) return 0;
+    uint32_t source = *T->sg_index;
+    Special *sp = new Special();
+    sp->kind = SP_GATHER; sp->offset = offset_var; sp->mask = mask_var;
+    ek_inc_ref_ext(offset_var); ek_inc_ref_ext(mask_var);
+    sp->size = T->sg_size; sp->permute = T->sg_permute;
+    uint32_t target = append_node(*T, ek_var_size(offset_var), "gather");
+    TEdge e; e.source = source; e.special = sp;
+    T->nodes[target].edges.push_back(e);
+    inc_ref_int(*T, source, target);
+    return target;
+}
+
+int ek_tape_append_scatter(ek_type t, uint32_t source, uint32_t offset_var, uint32_t mask_var, int scatter_add) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    if (T->sg_index == nullptr || source == 0) return 0;
+    uint32_t target_orig = *T->sg_index;
+    Special *sp = new Special();
+    sp->kind = SP_SCATTER; sp->offset = offset_var; sp->mask = mask_var;
+    ek_inc_ref_ext(offset_var); ek_inc_ref_ext(mask_var);
+    sp->size = T->sg_size; sp->scatter_add = scatter_add != 0;
+    uint32_t target_new = append_node(*T, T->sg_size, scatter_add ? "scatter_add" : "scatter");
+    TEdge e; e.source = source; e.special = sp;
+    T->nodes[target_new].edges.push_back(e);
+    inc_ref_int(*T, source, target_new);
+    if (target_orig != 0) {
+        uint32_t sa_node = target_new;
+        uint32_t one = v_literal(t, 1.0), weight;
+        if (!scatter_add && !T->sg_permute) {
+            /* weight zeroes the slots that were overwritten (autodiff.cpp:588-592) */
+            size_t es = ek_type_size(t);
+            void *p = ek_malloc(T->sg_size * es);
+            uint64_t one_bits = ek_ctx().vars[one].imm;
+            ek_fill(p, es, one_bits, T->sg_size);
+            weight = ek_var_register(t, T->sg_size, p, 1);
+            uint32_t zero = v_literal(t, 0.0);
+            ek_set_scatter_gather_operand(weight, 0);
+            uint32_t ptr = ek_var_register_ptr(p);
+            uint32_t h = v_op(EK_UINT64, EK_OP_SCATTER, ptr, offset_var, mask_var, ((uint64_t) es << 32) | zero);
+            ek_dec_ref_ext(ptr); ek_dec_ref_ext(zero);
+            ek_set_scatter_gather_operand(0, 0);
+            if (!h) return -1;
+            ek_var_mark_side_effect(h);
+            ek_var_mark_dirty(weight);
+        } else {
+            weight = one; ek_inc_ref_ext(one);
+        }
+        uint32_t in[2] = { target_new, target_orig }, w[2] = { one, weight };
+        target_new = ek_tape_append(t, "scatter_combine", T->sg_size, 2, in, w);
+        ek_dec_ref_ext(one); ek_dec_ref_ext(weight);
+        dec_ref_ext(*T, sa_node);
+        dec_ref_ext(*T, target_orig);
+    }
+    *T->sg_index = target_new;
+    return 0;
+}
+
+uint32_t ek_tape_append_psum(ek_type t, uint32_t src) {
+    Tape *T = tape_of(t); if (!T || src == 0) return 0;
+    TNode *s = node(*T, src); if (!s) return 0;
+    Special *sp = new Special(); sp->kind = SP_PSUM;
+    uint32_t target = append_node(*T, s->size, "psum");
+    TEdge e; e.source = src; e.special = sp;
+    T->nodes[target].edges.push_back(e);
+    inc_ref_int(*T, src, target);
+    return target;
+}
+
+uint32_t ek_tape_append_reverse(ek_type t, uint32_t src) {
+    Tape *T = tape_of(t); if (!T || src == 0) return 0;
+    TNode *s = node(*T, src); if (!s) return 0;
+    Special *sp = new Special(); sp->kind = SP_REVERSE;
+    uint32_t target = append_node(*T, s->size, "reverse");
+    TEdge e; e.source = src; e.special = sp;
+    T->nodes[target].edges.push_back(e);
+    inc_ref_int(*T, src, target);
+    return target;
+}
+
+void ek_tape_inc_ref_ext(ek_type t, uint32_t index) { Tape *T = tape_of(t); if (T) inc_ref_ext(*T, index); }
+void ek_tape_dec_ref_ext(ek_type t, uint32_t index) { Tape *T = tape_of(t); if (T) dec_ref_ext(*T, index); }
+
+int ek_tape_set_scatter_gather_operand(ek_type t, uint32_t *index, size_t size, int permute) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    if (index != nullptr && T->sg_index != nullptr) {
+        ek_set_error("set_scatter_gather_operand(): attempted to override an existing operand!");   /* autodiff.cpp:788-790 */
+        return -1;
+    }
+    T->sg_index = index; T->sg_size = size; T->sg_permute = permute != 0;
+    return 0;
+}
+
+int ek_tape_set_gradient(ek_type t, uint32_t index, uint32_t value_var, int backward) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    if (index == 0) {
+        ek_set_error("set_gradient(): no gradients are associated with this variable (a prior call to requires_gradient() is required.) ");
+        return -1;
+    }
+    if (!node(*T, index)) return -1;
+    dfs(*T, index, backward != 0, true);
+    TNode &n = *node(*T, index);
+    ek_inc_ref_ext(value_var);
+    set_grad(n, value_var);
+    if (n.size > 1 && ek_var_size(n.grad) == 1) return fix_grad_size(*T, n);
+    return 0;
+}
+
+int ek_tape_backward_static(ek_type t, int free_graph) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    bool saved = T->graph_simplification; T->graph_simplification = false;
+    int rc = backward_impl(*T, free_graph != 0);
+    T->graph_simplification = saved;
+    if (rc != 0) T->scheduled.clear();
+    return rc;
+}
+
+int ek_tape_forward_static(ek_type t, int free_graph) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    bool saved = T->graph_simplification; T->graph_simplification = false;
+    int rc = forward_impl(*T, free_graph != 0);
+    T->graph_simplification = saved;
+    if (rc != 0) T->scheduled.clear();
+    return rc;
+}
+
+int ek_tape_backward(ek_type t, uint32_t index, int free_graph) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    uint32_t one = v_literal(t, 1.0);
+    int rc = ek_tape_set_gradient(t, index, one, 1);
+    ek_dec_ref_ext(one);
+    if (rc != 0) return rc;
+    return ek_tape_backward_static(t, free_graph);
+}
+
+int ek_tape_forward(ek_type t, uint32_t index, int free_graph) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    uint32_t one = v_literal(t, 1.0);
+    int rc = ek_tape_set_gradient(t, index, one, 0);
+    ek_dec_ref_ext(one);
+    if (rc != 0) return rc;
+    return ek_tape_forward_static(t, free_graph);
+}
+
+uint32_t ek_tape_gradient(ek_type t, uint32_t index) {
+    Tape *T = tape_of(t); if (!T) return 0;
+    if (index == 0) {
+        ek_set_error("No gradient was computed for this variable! (a call to requires_gradient() is necessary.)");   /* autodiff.cpp:797-800 */
+        return 0;
+    }
+    TNode *n = node(*T, index); if (!n) return 0;
+    ek_set_error("");
+    return n->grad;
+}
+
+int ek_tape_set_label(ek_type t, uint32_t index, const char *label) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    if (index == 0) return 0;
+    TNode *n = node(*T, index); if (!n) return -1;
+    n->label = "'" + std::string(label) + "'";
+    if (n->grad) ek_var_set_label(n->grad, (std::string(label) + ".grad").c_str());
+    return 0;
+}
+
+void ek_tape_push_prefix(ek_type t, const char *prefix) { Tape *T = tape_of(t); if (T) T->prefix.push_back(prefix); }
+int ek_tape_pop_prefix(ek_type t) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    if (T->prefix.empty()) { ek_set_error("pop_prefix(): prefix list is already empty!"); return -1; }
+    T->prefix.pop_back();
+    return 0;
+}
+void ek_tape_set_log_level(ek_type t, uint32_t level) { Tape *T = tape_of(t); if (T) T->log_level = level; }
+void ek_tape_set_graph_simplification(ek_type t, int enable) { Tape *T = tape_of(t); if (T) T->graph_simplification = enable != 0; }
+
+int ek_tape_simplify(ek_type t) {
+    Tape *T = tape_of(t); if (!T) return -1;
+    /* greedy vertex elimination (autodiff.cpp:990-1074) is a "next" row of SURVEY 8f; the
+       level-batched backward pass does not depend on it for correctness */
+    T->is_simplified = true;
+    return 0;
+}
+
+char *ek_tape_graphviz(ek_type t, size_t n, const uint32_t *indices) {
+    Tape *T = tape_of(t); if (!T) return nullptr;
+    /* autodiff.cpp:1076-1163 */
+    std::ostringstream oss;
+    oss << "digraph {\n  rankdir=BT;\n  graph [dpi=50];\n  node [shape=record fontname=Consolas];\n  edge [fontname=Consolas];\n";
+    std::set<uint32_t> seen; std::vector<uint32_t> stack(indices, indices + n);
+    while (!stack.empty()) {
+        uint32_t k = stack.back(); stack.pop_back();
+        if (k == 0 || seen.count(k)) continue;
+        auto it = T->nodes.find(k); if (it == T->nodes.end()) continue;
+        seen.insert(k);
+        const TNode &nd = it->second;
+        oss << "  " << k << " [label=\"" << nd.label << (nd.size == 1 ? " [s]" : "") << "\\n#" << k << " [E/I: " << nd.ref_ext << "/" << nd.ref_int << "]\""
+            << (nd.edges.empty() ? " fillcolor=salmon style=filled" : "") << "];\n";
+        for (const TEdge &e : nd.edges) {
+            oss << "  " << k << " -> " << e.source << (e.special ? " [color=red]" : "") << ";\n";
+            stack.push_back(e.source);
+        }
+    }
+    oss << "}";
+    return strdup(oss.str().c_str());
+}
+
+char *ek_tape_whos(ek_type t) {
+    Tape *T = tape_of(t); if (!T) return nullptr;
+    std::ostringstream oss;
+    oss << "\n  ID        E/I Refs   Size        Label\n  ========================================\n";
+    std::vector<uint32_t> ids;
+    for (auto &kv : T->nodes) ids.push_back(kv.first);
+    std::sort(ids.begin(), ids.end());
+    for (uint32_t id : ids) {
+        const TNode &n = T->nodes[id];
+        char line[256];
+        snprintf(line, sizeof(line), "  %-9u %u / %-6u %-11u %s\n", id, n.ref_ext, n.ref_int, n.size, n.label.c_str());
+        oss << line;
+    }
+    oss << "  ========================================\n";
+    return strdup(oss.str().c_str());
+}
+
+size_t ek_tape_node_count(ek_type t) { Tape *T = tape_of(t); return T ? T->nodes.size() : 0; }
+
+void ek_tape_clear(ek_type t) {
+    int i = t == EK_FLOAT64 ? 1 : 0;
+    Tape *T = g_tapes[i];
+    if (!T) return;
+    std::vector<uint32_t> ids;
+    for (auto &kv : T->nodes) ids.push_back(kv.first);
+    for (uint32_t id : ids) {
+        auto it = T->nodes.find(id);
+        if (it == T->nodes.end()) continue;
+        for (TEdge &e : it->second.edges) release_edge(e);
+        if (it->second.grad) ek_dec_ref_ext(it->second.grad);
+    }
+    T->nodes.clear();
+    T->scheduled.clear();
+    T->sg_index = nullptr;
+}
+
+} /* extern "C" */
