@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Enoki backend.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (N=1 and every rank of N>1, weak scaling): BASELINE.json configs[1] =
+"CUDAArray<float> 64M-elem fused arith+exp/sin chain, cuda_eval()":
+    t = fmadd(x0,x1,x2); u = exp(-(t*t)); v = sin(fmadd(x3,u,x0)); out = fmadd(v,x1,sqrt(abs(t)))
+on N = 2^26 fp32 elements per GPU.  One step = record the expression through
+the C ABI, cuda_eval() it (one fused sweep kernel: 4 input streams + 1 output stream = 20 B/elem),
+plus a fused hsum of the output whose scalar is all-reduced over NCCL when N>1 (the only
+cross-GPU value).  Metric: M array-ops/s (DAG nodes x elements / s, jit.cu:1219-1222).
+
+The JSON line also carries
+  roofline      -- the sweep kernel's algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  backward      -- the C4 tape (10 240 nodes / 20 224 edges, node width 131 072): M edge-adjoints/s
+  e2e           -- same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timing)
+  cpu_baseline  -- the reference's own CPU path (oracle/_ref) timed on this box's host cores
+`--impl reference` times the reference CPU path alone (rank 0 only).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ELEMS = 1 << 26
+C2_NODES = 9            # fma, mul, neg, exp, fma, sin, abs, sqrt, fma (what the runtime counts as ops=)
+C2_BYTES_PER_ELEM = 20  # 4 input streams + 1 output stream, fp32
+C4 = dict(levels=80, per_level=128, width=131072)
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Sample nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, smax, reasons = [], None, set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference CPU arm
+def load_ref(fast=True):
+    name = "libenoki_ref_fast.so" if fast else "libenoki_ref.so"
+    path = os.path.join(ROOT, "oracle", "_ref", name)
+    if os.path.exists(path):
+        lib = ctypes.CDLL(path)
+        lib.ref_c2_time.restype = ctypes.c_double
+        lib.ref_c2_time_vectorized.restype = ctypes.c_double
+        lib.ref_info.restype = ctypes.c_char_p
+        return lib, "reference"
+    path = os.path.join(ROOT, "oracle", "liboracle.so")
+    lib = ctypes.CDLL(path)
+    lib.or_c2_time.restype = ctypes.c_double
+    return lib, "port"
+
+
+def cpu_c2(sample_elems, reps, threads):
+    """Time the reference's CPU implementation of C2 on `threads` host threads, each on its own
+    slice of `sample_elems` elements (Enoki is single-threaded by construction; the split is the
+    embarrassingly-parallel one of BASELINE.md section 3).  Returns elements/s (aggregate)."""
+    lib, kind = load_ref(True)
+    per = sample_elems // threads
+    rng = np.random.default_rng(0)
+    bufs = []
+    for _ in range(threads):
+        xs = [np.ascontiguousarray(rng.uniform(-4, 4, per).astype(np.float32)) for _ in range(4)]
+        out = np.zeros(per, np.float32)
+        bufs.append((xs, out))
+    best = [0.0] * threads
+
+    def work(t):
+        xs, out = bufs[t]
+        if kind == "reference":
+            # the reference's own fastest CPU form: the fused vectorize() loop (dynamic.h:1025-1074)
+            best[t] = lib.ref_c2_time_vectorized(P(xs[0]), P(xs[1]), P(xs[2]), P(xs[3]), P(out), ctypes.c_size_t(per), reps)
+        else:
+            best[t] = lib.or_c2_time(P(xs[0]), P(xs[1]), P(xs[2]), P(xs[3]), P(out), ctypes.c_size_t(per), reps)
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.time()
+    for th in ths: th.start()
+    for th in ths: th.join()
+    wall = time.time() - t0
+    slowest = max(best)
+    return per * threads / slowest, kind, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 1 << 24
+    reps_per_step = 1
+    lib, kind = load_ref(True)
+    # warm-up + K timed "steps", each a bounded sample of the workload on all host threads
+    for _ in range(max(args.warmup, 1)):
+        cpu_c2(sample, 1, cores)
+    t0 = time.time()
+    rates = []
+    for _ in range(args.steps):
+        r, kind, _ = cpu_c2(sample, reps_per_step, cores)
+        rates.append(r)
+    wall = time.time() - t0
+    elems_per_s = float(np.median(rates))
+    value = elems_per_s * C2_NODES / 1e6
+    line = {
+        "impl": "reference", "metric": "M array-ops/s (eval)", "value": value, "unit": "M array-ops/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: CUDAArray<float> 64M-elem fused arith+exp/sin chain (CPU: DynamicArray<Packet<float,8>> vectorize() form)",
+                   "elems": N_ELEMS, "nodes": C2_NODES},
+        "cpu_baseline": {"value": value, "unit": "M array-ops/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} of {N_ELEMS} elements per step, split over {cores} threads, AVX2+FMA -ffp-contract=fast"},
+        "e2e": {"value": value, "unit": "M array-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--elems", type=int, default=N_ELEMS, help="elements per GPU (default: the BASELINE config, 2^26)")
+    ap.add_argument("--skip-backward", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import enoki_b200 as ek
+    from enoki_b200 import Float32, fmadd, exp, sin, sqrt, hsum
+    L = ek.lib()
+    if L.ek_device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device visible -- enoki_b200 has no CPU fallback")
+    L.ek_set_device(local_rank)
+    assert L.ek_init() == 0, L.ek_last_error()
+    torch.cuda.set_device(local_rank)
+    ext_stream = torch.cuda.ExternalStream(L.ek_stream(), device=torch.device("cuda", local_rank))
+
+    n = args.elems
+    # ---- synthetic inputs, generated on the device by the backend itself (resident in HBM)
+    idx = ek.UInt32.arange(n)
+
+    def mk(k):
+        h = idx * np.uint32(2654435761 + 2 * k) + np.uint32(12345 * (k + 1) + rank)
+        return fmadd(Float32(h >> 8), Float32(8.0 / (1 << 24)), Float32(-4.0))
+    x = [mk(k) for k in range(4)]
+    ek.cuda_eval(); ek.cuda_sync()
+    del idx
+
+    class DevScalar:
+        """expose a 4-byte device buffer to torch (NCCL all-reduce of the loss scalar)"""
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (1,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    def step(reduce_scalar=True):
+        t = fmadd(x[0], x[1], x[2])
+        u = exp(-(t * t))
+        v = sin(fmadd(x[3], u, x[0]))
+        out = fmadd(v, x[1], sqrt(abs(t)))
+        del t, u, v
+        s = hsum(out) if reduce_scalar else None
+        ek.cuda_eval()
+        if world > 1 and s is not None:
+            with torch.cuda.stream(ext_stream):
+                ten = torch.as_tensor(DevScalar(L.ek_var_ptr(s.index)), device=f"cuda:{local_rank}")
+                dist.all_reduce(ten)
+        return out, s
+
+    def barrier():
+        ek.cuda_sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.ek_stats_reset()
+    barrier()
+    L.ek_timer_start()
+    t0 = time.time()
+    keep = None
+    for _ in range(args.steps):
+        keep = step()
+    ms = L.ek_timer_stop()
+    barrier()
+    wall_ms = 1e3 * (time.time() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    st = ek.stats()
+    launches = int(st.launches)
+    if dist is not None:
+        tt = torch.tensor([ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    ms_per_step = ms / args.steps
+    value = world * n * C2_NODES / (ms_per_step * 1e-3) / 1e6
+    loss_val = float(keep[1].numpy()[0])
+    del keep
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launch stream
+    L.ek_set_timing(1)
+    L.ek_stats_reset()
+    for _ in range(5):
+        o, s = step(reduce_scalar=False)
+        del o, s
+    stt = ek.stats()
+    L.ek_set_timing(0)
+    kern_ms = stt.total_kernel_ms / max(int(stt.sweep_launches), 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = C2_BYTES_PER_ELEM * n / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "kernel": "ek_sweep_kernel<8>", "kernel_ms": kern_ms,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"}
+
+    # ---- e2e: pinned host buffers, H2D of the 4 inputs + D2H of the result inside the timed region
+    e2e = None
+    if rank == 0 or world > 1:
+        hb = [L.ek_host_malloc(n * 4) for _ in range(5)]
+        for k in range(4):
+            L.ek_memcpy_from_device(hb[k], L.ek_var_ptr(x[k].index), n * 4)
+
+        def e2e_step():
+            xs = []
+            for k in range(4):
+                d = L.ek_malloc(n * 4)
+                L.ek_memcpy_to_device_async(d, hb[k], n * 4)
+                xs.append(Float32.map(d, n, True))
+            t = fmadd(xs[0], xs[1], xs[2])
+            out = fmadd(sin(fmadd(xs[3], exp(-(t * t)), xs[0])), xs[1], sqrt(abs(t)))
+            del t
+            ek.cuda_eval()
+            L.ek_memcpy_from_device(hb[4], L.ek_var_ptr(out.index), n * 4)
+
+        e2e_steps = max(3, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        te = time.time()
+        for _ in range(e2e_steps):
+            e2e_step()
+        ek.cuda_sync()
+        e2e_ms = 1e3 * (time.time() - te) / e2e_steps
+        if dist is not None:
+            tt = torch.tensor([e2e_ms], device=f"cuda:{local_rank}")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item())
+        e2e = {"value": world * n * C2_NODES / (e2e_ms * 1e-3) / 1e6, "unit": "M array-ops/s",
+               "h2d_bytes_per_step": 4 * n * 4, "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_ms}
+        for p in hb:
+            L.ek_host_free(p)
+
+    # ---- backward: C4 tape (per rank), K' passes of backward(free_graph=False)
+    backward = None
+    if not args.skip_backward:
+        backward = bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs)
+
+    # ---- CPU baseline beside it (rank 0, bounded sample)
+    cpu = None
+    if rank == 0 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        r, kind, wall = cpu_c2(1 << 24, 3, cores)
+        r1, _, wall1 = cpu_c2(1 << 22, 3, 1)
+        cpu = {"value": r * C2_NODES / 1e6, "unit": "M array-ops/s", "cores": cores, "kind": kind,
+               "sample": f"2^24 of 2^26 elements split over {cores} threads (vectorize() form, best of 3); single thread on 2^22: "
+                         f"{r1 * C2_NODES / 1e6:.1f} M array-ops/s"}
+
+    if rank == 0:
+        line = {
+            "metric": "M array-ops/s (eval)", "value": value, "unit": "M array-ops/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: CUDAArray<float> 64M-elem fused arith+exp/sin chain, cuda_eval() (+ fused hsum, NCCL all-reduce of the scalar when N>1)",
+                       "elems_per_gpu": n, "nodes": C2_NODES, "bytes_per_elem": C2_BYTES_PER_ELEM,
+                       "l2": "inputs 4 x 256 MiB per step exceed the 126 MB L2 (no explicit flush needed)",
+                       "parallelism": f"element-range sharding x{world}, one rank per GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "backward": backward, "wall_ms_per_step": wall_ms / args.steps, "loss_checksum": loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
+    """80 levels x 128 nodes, node width 131072, 2 in-edges per non-leaf node to random
+    nodes of the previous level, materialised fp32 weights U(0.5,1.5) with 1% exact zeros, loss = hsum
+    over the last level.  Algorithmic traffic: weights once + adjoints written once and read once per
+    out-edge (10.0 B / edge-adjoint).  Timed: backward() only (the tape is built once)."""
+    from enoki_b200 import Float32, UInt32, fmadd, select
+    F32 = ek.EK_FLOAT32
+    Lv, K, w = C4["levels"], C4["per_level"], C4["width"]
+    rng = np.random.default_rng(1234 + rank)
+    idx = UInt32.arange(w)
+    ids = [[0] * K for _ in range(Lv)]
+    keep = []
+    n_edges = 0
+    one = Float32(1.0)
+    for lvl in range(Lv):
+        for k in range(K):
+            if lvl == 0:
+                ids[lvl][k] = L.ek_tape_append_leaf(F32, w)
+                continue
+            node = L.ek_tape_append_node(F32, w, b"n")
+            ids[lvl][k] = node
+            for p in sorted(rng.choice(K, 2, replace=False)):
+                seed = int(rng.integers(1, 2**31))
+                h = idx * np.uint32(2654435761) + np.uint32(seed)
+                h = (h ^ (h >> 15)) * np.uint32(2246822519)
+                wt = fmadd(Float32((h >> 8)), Float32(1.0 / (1 << 24)), Float32(0.5))
+                wt = select((h & np.uint32(127)) < UInt32(1), Float32(0.0), wt)     # ~1% exact zeros
+                keep.append(wt)
+                assert L.ek_tape_append_edge(F32, ids[lvl - 1][int(p)], node, wt.index) == 0
+                n_edges += 1
+        ek.cuda_eval()          # materialise this level's weights (keeps the trace small)
+    loss = L.ek_tape_append_node(F32, 1, b"loss")
+    for k in range(K):
+        assert L.ek_tape_append_edge(F32, ids[Lv - 1][k], loss, one.index) == 0
+    ek.cuda_sync()
+    n_nodes = Lv * K
+
+    def run(free):
+        assert L.ek_tape_backward(F32, loss, int(free)) == 0, L.ek_last_error()
+
+    run(False); run(False)
+    ek.cuda_sync()
+    steps = 5
+    L.ek_stats_reset()
+    L.ek_timer_start()
+    for _ in range(steps):
+        run(False)
+    ms = L.ek_timer_stop()
+    st = ek.stats()
+    if dist is not None:
+        tt = torch.tensor([ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    ms_per = ms / steps
+    edge_adjoints = int(st.edge_adjoints) // steps
+    # reachable sub-graph only: the runtime counts exactly the (edge, element) pairs it processed
+    bytes_alg = 10.0 * edge_adjoints
+    res = {"metric": "M edge-adjoints/s (backward)", "value": world * edge_adjoints / (ms_per * 1e-3) / 1e6,
+           "unit": "M edge-adjoints/s", "ms_per_backward": ms_per, "nodes": n_nodes + 1, "edges": n_edges + K,
+           "edge_adjoints_per_backward": edge_adjoints, "node_width": w,
+           "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms_per * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": bytes_alg / (ms_per * 1e-3) / 1e9 / peak_gbs, "bytes_per_edge_adjoint": 10.0,
+                        "weights_only_frac": 4.0 * edge_adjoints / (ms_per * 1e-3) / 1e9 / peak_gbs,
+                        "note": "whole backward() incl. host scheduling and 80 per-level launches"},
+           "launches_per_backward": int(st.adjoint_launches) // steps}
+    # final pass frees the graph; leaf gradients stay readable
+    run(True)
+    g = L.ek_tape_gradient(F32, ids[0][0])
+    if g:
+        L.ek_inc_ref_ext(g)
+        res["leaf0_grad_checksum"] = float(Float32.from_index(g).numpy()[:1024].astype(np.float64).sum())
+    for lvl in range(Lv):
+        for k in range(K):
+            L.ek_tape_dec_ref_ext(F32, ids[lvl][k])
+    L.ek_tape_dec_ref_ext(F32, loss)
+    del keep
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,7 @@ static_assert(sizeof(EkSweepArgs) <= 4096, "EkSweepArgs must fit the classic ker
 #include <functional>
 #include <sstream>
 #include <unordered_set>
+#include <memory>
 
 namespace {
 
@@ -43,6 +44,7 @@ struct Group {
     std::vector<uint32_t> roots;
     std::vector<uint32_t> sched;
     std::unordered_set<uint32_t> visited;
+    std::unordered_set<uint32_t> boundary;    /* inputs produced by an earlier launch of the same eval */
 };
 
 struct Output { uint32_t var; uint32_t argw; size_t bytes; };
@@ -65,7 +67,10 @@ struct Assembled {
     struct DescFix { uint32_t argw; uint32_t count_limit; };
     std::vector<uint32_t> copies_fix;           /* argw index of Desc.copies (set from config) */
     std::string error;
+    bool resource_error = false;     /* a limit was hit: the caller may split the group and retry */
 };
+
+#define EK_STAGE_UNIT_BUDGET 8u     /* slot units of TMA-staged inputs per pipeline stage */
 
 struct Config { int V; uint32_t T; uint32_t stages; uint32_t ctas_per_sm; size_t smem; uint32_t off_bar, off_prog, off_extra, off_slots; bool prog_in_smem; };
 
@@ -198,6 +203,7 @@ struct Assembler {
     std::unordered_map<uint64_t, uint32_t> lit32, lit64;
     std::vector<uint8_t> slot_used;
     std::unordered_map<uint32_t, uint32_t> red_acc;    /* reduce var -> accumulator slot */
+    std::unordered_set<uint32_t> direct;               /* wide inputs loaded with ld.global instead of TMA staging */
     uint32_t acc_var = 0;
     uint32_t cur_e = 0;
 
@@ -252,6 +258,7 @@ struct Assembler {
     static uint16_t staged_code(uint32_t unit) { return (uint16_t) (0x4000u | unit); }
 
     bool fail(const std::string &m) { if (out.error.empty()) out.error = m; return false; }
+    bool fail_resource(const std::string &m) { out.resource_error = true; return fail(m); }
 
     uint16_t operand(uint32_t v) {
         if (v == acc_var) return EK_OPND_ACC;
@@ -301,6 +308,19 @@ struct Assembler {
     }
 
     bool run() {
+        /* ---- pass 0: wide inputs beyond the staging budget are loaded directly (ld.global) ---- */
+        {
+            uint32_t units = 0, count = 0;
+            for (uint32_t idx : g.sched) {
+                const EkVariable &v = var(idx);
+                bool is_input = (v.data != nullptr && !v.direct_pointer) || boundary_input(idx);
+                if (!is_input || v.size == 1 || !wide()) continue;
+                uint32_t u = ek_type_size(v.type) == 8 ? 2 : 1;
+                if (count >= EK_MAX_STAGED || units + u > EK_STAGE_UNIT_BUDGET) direct.insert(idx);
+                else { units += u; ++count; }
+            }
+        }
+
         /* ---- pass 1: classify inputs, count uses ---- */
         uint32_t e = 0;
         std::vector<uint32_t> emits(g.sched.size(), 0);
@@ -309,7 +329,7 @@ struct Assembler {
             const EkVariable &v = var(idx);
             bool is_input = v.data != nullptr || v.direct_pointer || boundary_input(idx);
             bool emitting;
-            if (is_input) emitting = false;
+            if (is_input) emitting = direct.count(idx) != 0;
             else if (v.op == EK_OP_LITERAL) emitting = lit_emits(idx);
             else emitting = true;
             if (emitting) {
@@ -338,13 +358,16 @@ struct Assembler {
             } else if (v.data != nullptr || binput) {
                 size_t es = ek_type_size(v.type);
                 if (v.size == 1 || !wide()) {
-                    if (out.scalars.size() >= EK_MAX_SCALAR) return fail("too many scalar inputs in one kernel (limit " + std::to_string(EK_MAX_SCALAR) + ")");
+                    if (out.scalars.size() >= EK_MAX_SCALAR) return fail_resource("too many scalar inputs in one kernel (limit " + std::to_string(EK_MAX_SCALAR) + ")");
                     uint32_t sidx = (uint32_t) out.scalars.size();
                     out.scalars.push_back({ idx });
                     loc[idx] = { Loc::UNI, (uint16_t) (0x8000u | 0x1000u | (2u * sidx)) };   /* rebased in finish */
+                } else if (direct.count(idx)) {
+                    if (v.size != g.size) return fail("encountered arrays of incompatible size");
+                    out.bytes_in += (uint64_t) v.size * es;       /* emitted as LDG in pass 2 */
                 } else {
                     if (v.size != g.size) return fail("encountered arrays of incompatible size");
-                    if (out.staged.size() >= EK_MAX_STAGED) return fail("too many input arrays in one kernel (limit " + std::to_string(EK_MAX_STAGED) + "); call cuda_eval() earlier");
+                    if (out.staged.size() >= EK_MAX_STAGED) return fail_resource("too many input arrays in one kernel (limit " + std::to_string(EK_MAX_STAGED) + "); call cuda_eval() earlier");
                     uint32_t units = es == 8 ? 2 : 1;
                     out.staged.push_back({ idx, (uint16_t) unit, (uint8_t) es });
                     loc[idx] = { Loc::STAGED, (uint16_t) unit };
@@ -394,6 +417,26 @@ struct Assembler {
         for (size_t i = 0; i < g.sched.size(); ++i) {
             uint32_t idx = g.sched[i];
             const EkVariable &v = var(idx);
+            if (direct.count(idx)) {
+                cur_e = emits[i];
+                int op;
+                switch (v.type) {
+                    case EK_BOOL: case EK_UINT8: op = DOP_LDG_U8; break;
+                    case EK_INT8: op = DOP_LDG_S8; break;
+                    case EK_UINT16: op = DOP_LDG_U16; break;
+                    case EK_INT16: op = DOP_LDG_S16; break;
+                    case EK_FLOAT16: return fail("Float16 arrays are not supported");
+                    case EK_INT32: case EK_UINT32: case EK_FLOAT32: op = DOP_LDG_32; break;
+                    default: op = DOP_LDG_64; break;
+                }
+                uint32_t pa = arg_ptr(idx, false);
+                EkInstr in = mk(op, EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, uni_arg(pa) & 0x7fffu);
+                in.flags |= 0x4000u;
+                place_result(in, idx, true);
+                out.body.push_back(in);
+                acc_var = idx;
+                continue;
+            }
             if (v.data != nullptr || v.direct_pointer || boundary_input(idx)) continue;
             if (v.op == EK_OP_LITERAL && !lit_emits(idx)) continue;
             cur_e = emits[i];
@@ -413,7 +456,7 @@ struct Assembler {
        scalar) and is therefore an input here */
     bool boundary_input(uint32_t idx) const {
         if (var(idx).data != nullptr) return false;
-        return forced.count(idx) && g.visited.count(idx) == 0;
+        return g.boundary.count(idx) != 0;
     }
 
     bool emit_var(uint32_t idx, uint32_t pos) {
@@ -450,7 +493,7 @@ struct Assembler {
                 case EK_OP_ANY: kind = EK_RED_MAX; cls = EK_RC_U32; break;
                 default: kind = EK_RED_SUM; cls = EK_RC_U32; break;   /* COUNT */
             }
-            if (out.n_red >= EK_MAX_RED) return fail("too many reductions in one kernel");
+            if (out.n_red >= EK_MAX_RED) return fail_resource("too many reductions in one kernel");
             bool w64 = cls >= EK_RC_F64;
             uint32_t ridx = out.n_red++;
             uint32_t acc = red_acc[idx];                 /* reserved in run(); never freed */
@@ -659,8 +702,8 @@ struct Assembler {
     bool finish() {
         uint32_t n_lit = (uint32_t) out.lits.size();
         uint32_t n_arg = (uint32_t) out.argw.size();
-        if (n_arg > EK_MAX_ARGW) return fail("too many kernel arguments; call cuda_eval() earlier");
-        if (n_lit + n_arg + 2 * out.scalars.size() >= 0x1000u) return fail("uniform pool overflow");
+        if (n_arg > EK_MAX_ARGW) return fail_resource("too many kernel arguments; call cuda_eval() earlier");
+        if (n_lit + n_arg + 2 * out.scalars.size() >= 0x1000u) return fail_resource("uniform pool overflow");
         out.n_tmp = (uint32_t) slot_used.size();
         auto rebase_code = [&](uint16_t code) -> uint16_t {
             if (code == EK_OPND_NONE || code == EK_OPND_ACC) return code;
@@ -768,8 +811,12 @@ struct Planner {
         uint32_t p = phase(idx);
         Group &g = groups[{ p, sweep_size(idx) }];
         g.phase = p; g.size = sweep_size(idx);
+        collect(g, idx, &work);
+    }
+
+    /* DFS post-order from `idx` into group `g`, heavier subtree first (jit.cu:1385-1416) */
+    void collect(Group &g, uint32_t idx, std::vector<uint32_t> *work) {
         if (g.visited.count(idx)) return;
-        /* DFS post-order, heavier subtree first (jit.cu:1385-1416) */
         struct Frame { uint32_t idx; uint32_t deps[4]; int n; int i; };
         std::vector<Frame> stack;
         auto push = [&](uint32_t i) {
@@ -791,11 +838,11 @@ struct Planner {
                 uint32_t d = f.deps[f.i++];
                 if (is_boundary(d, f.idx) || stored_earlier(d, g.phase)) {
                     /* produced by an earlier launch: becomes an input here and a root there */
-                    if (!forced.count(d)) { forced.insert(d); work.push_back(d); }
-                    if (!g.visited.count(d)) { /* appears in the schedule as an input */
-                        g.sched.push_back(d);
-                        g.visited.insert(d);      /* NB: visited but "boundary" -- see boundary set */
-                        boundary_of[&g].insert(d);
+                    if (!forced.count(d)) { forced.insert(d); if (work) work->push_back(d); }
+                    if (!g.visited.count(d)) {
+                        g.sched.push_back(d);          /* appears in the schedule as an input */
+                        g.visited.insert(d);
+                        g.boundary.insert(d);
                     }
                 } else push(d);
                 continue;
@@ -805,7 +852,6 @@ struct Planner {
         }
         g.roots.push_back(idx);
     }
-    std::unordered_map<const Group *, std::unordered_set<uint32_t>> boundary_of;
 };
 
 size_t smem_layout(const Assembled &a, Config &cfg, size_t n_uni) {
@@ -946,23 +992,35 @@ static int eval_impl(bool dry, std::string *dump) {
         plan.add_root(idx, work);
     }
 
-    /* boundary inputs must not be treated as computed in the group that merely reads them */
-    for (auto &kv : plan.groups) {
-        Group &g = kv.second;
-        auto it = plan.boundary_of.find(&g);
-        if (it != plan.boundary_of.end()) for (uint32_t b : it->second) g.visited.erase(b);
-    }
-
     /* assemble every group first so that user errors leave the trace untouched */
+    std::vector<std::unique_ptr<Group>> split_groups;
     std::vector<std::pair<Group *, Assembled>> launches;
-    for (auto &kv : plan.groups) {                       /* ordered by (phase asc, size asc) */
-        Group &g = kv.second;
-        if (g.sched.empty()) continue;
+    std::string asm_error;
+    /* assemble `g`; when a per-kernel limit is hit (slots, inputs, arguments ...) split its roots in
+       two and retry -- shared sub-expressions are then recomputed, exactly as the reference does
+       across kernels of different sizes */
+    std::function<bool(Group &)> assemble_group = [&](Group &g) -> bool {
+        if (g.sched.empty()) return true;
+        if (g.size > 0xffffffffull) { asm_error = "arrays with more than 2^32-1 entries are not supported (jit.cu:1066,1090)"; return false; }
         Assembler as(ctx, g, plan.forced, dry);
-        if (g.size > 0xffffffffull) { ek_set_error("ek_eval(): arrays with more than 2^32-1 entries are not supported (jit.cu:1066,1090)"); return -1; }
-        if (!as.run()) { ek_set_error("ek_eval(): " + as.out.error); return -1; }
-        launches.emplace_back(&g, std::move(as.out));
-    }
+        bool ok = as.run();
+        Config cfg; std::string cerr;
+        if (ok && !choose_config(ctx, as.out, g.size, cfg, cerr)) { ok = false; as.out.error = cerr; as.out.resource_error = true; }
+        if (ok) { launches.emplace_back(&g, std::move(as.out)); return true; }
+        if (!as.out.resource_error || g.roots.size() < 2) { asm_error = as.out.error; return false; }
+        size_t half = g.roots.size() / 2;
+        for (int part = 0; part < 2; ++part) {
+            split_groups.emplace_back(new Group());
+            Group &sub = *split_groups.back();
+            sub.phase = g.phase; sub.size = g.size;
+            size_t lo = part == 0 ? 0 : half, hi = part == 0 ? half : g.roots.size();
+            for (size_t r = lo; r < hi; ++r) plan.collect(sub, g.roots[r], nullptr);
+            if (!assemble_group(sub)) return false;
+        }
+        return true;
+    };
+    for (auto &kv : plan.groups)                         /* ordered by (phase asc, size asc) */
+        if (!assemble_group(kv.second)) { ek_set_error("ek_eval(): " + asm_error); return -1; }
     /* within a phase launch the largest size first (jit.cu:1450) */
     std::stable_sort(launches.begin(), launches.end(), [](const auto &a, const auto &b) {
         if (a.first->phase != b.first->phase) return a.first->phase < b.first->phase;
