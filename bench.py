@@ -101,17 +101,26 @@ def load_ref(fast=True):
     return lib, "port"
 
 
+def aligned_f32(n, align=64):
+    """float32 buffer whose address is `align`-byte aligned (DynamicArray::map needs packet alignment)."""
+    raw = np.zeros(n * 4 + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * 4].view(np.float32)
+
+
 def cpu_c2(sample_elems, reps, threads):
     """Time the reference's CPU implementation of C2 on `threads` host threads, each on its own
     slice of `sample_elems` elements (Enoki is single-threaded by construction; the split is the
     embarrassingly-parallel one of BASELINE.md section 3).  Returns elements/s (aggregate)."""
     lib, kind = load_ref(True)
-    per = sample_elems // threads
+    per = (sample_elems // threads) // 16 * 16
     rng = np.random.default_rng(0)
     bufs = []
     for _ in range(threads):
-        xs = [np.ascontiguousarray(rng.uniform(-4, 4, per).astype(np.float32)) for _ in range(4)]
-        out = np.zeros(per, np.float32)
+        xs = []
+        for _k in range(4):
+            a = aligned_f32(per); a[:] = rng.uniform(-4, 4, per).astype(np.float32); xs.append(a)
+        out = aligned_f32(per)
         bufs.append((xs, out))
     best = [0.0] * threads
 
