@@ -19,7 +19,7 @@
  *     phase, so `x / hsum(x)` needs no host round trip.
  */
 #include "ek_internal.h"
-static_assert(sizeof(EkSweepArgs) <= 4096, "EkSweepArgs must fit the classic kernel parameter space");
+static_assert(sizeof(EkSweepArgs) <= 32000, "EkSweepArgs must fit the 32 KB kernel parameter space (CUDA >= 12.1, sm_70+)");
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,9 +108,9 @@ int pick_op(ek_op op, ek_type vt, ek_type at /* operand type */) {
     Cls c = cls_of(op >= EK_OP_GT && op <= EK_OP_NE ? at : vt);
     if (c == C_BAD) return -1;
     switch (op) {
-        case EK_OP_MOV:   return SEL(DOP_MOV_32, DOP_MOV_64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
+        case EK_OP_MOV:   return SEL(DOP_LOAD_32, DOP_LOAD_64, DOP_LOAD_32, DOP_LOAD_32, DOP_LOAD_64, DOP_LOAD_64);
         case EK_OP_NEG:   return SEL(DOP_NEG_F32, DOP_NEG_F64, DOP_NEG_I32, DOP_NEG_I32, DOP_NEG_I64, DOP_NEG_I64);
-        case EK_OP_ABS:   return SEL(DOP_ABS_F32, DOP_ABS_F64, DOP_ABS_I32, DOP_MOV_32, DOP_ABS_I64, DOP_MOV_64);
+        case EK_OP_ABS:   return SEL(DOP_ABS_F32, DOP_ABS_F64, DOP_ABS_I32, DOP_LOAD_32, DOP_ABS_I64, DOP_LOAD_64);
         case EK_OP_SQRT:  return SEL(DOP_SQRT_F32, DOP_SQRT_F64, -1, -1, -1, -1);
         case EK_OP_RCP:   return SEL(DOP_RCP_F32, DOP_RCP_F64, -1, -1, -1, -1);
         case EK_OP_RSQRT: return SEL(DOP_RSQRT_F32, DOP_RSQRT_F64, -1, -1, -1, -1);
@@ -118,10 +118,10 @@ int pick_op(ek_op op, ek_type vt, ek_type at /* operand type */) {
         case EK_OP_LOG:   return SEL(DOP_LOG_F32, DOP_LOG_F64, -1, -1, -1, -1);
         case EK_OP_SIN:   return SEL(DOP_SIN_F32, DOP_SIN_F64, -1, -1, -1, -1);
         case EK_OP_COS:   return SEL(DOP_COS_F32, DOP_COS_F64, -1, -1, -1, -1);
-        case EK_OP_FLOOR: return SEL(DOP_FLOOR_F32, DOP_FLOOR_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
-        case EK_OP_CEIL:  return SEL(DOP_CEIL_F32, DOP_CEIL_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
-        case EK_OP_ROUND: return SEL(DOP_ROUND_F32, DOP_ROUND_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
-        case EK_OP_TRUNC: return SEL(DOP_TRUNC_F32, DOP_TRUNC_F64, DOP_MOV_32, DOP_MOV_32, DOP_MOV_64, DOP_MOV_64);
+        case EK_OP_FLOOR: return SEL(DOP_FLOOR_F32, DOP_FLOOR_F64, DOP_LOAD_32, DOP_LOAD_32, DOP_LOAD_64, DOP_LOAD_64);
+        case EK_OP_CEIL:  return SEL(DOP_CEIL_F32, DOP_CEIL_F64, DOP_LOAD_32, DOP_LOAD_32, DOP_LOAD_64, DOP_LOAD_64);
+        case EK_OP_ROUND: return SEL(DOP_ROUND_F32, DOP_ROUND_F64, DOP_LOAD_32, DOP_LOAD_32, DOP_LOAD_64, DOP_LOAD_64);
+        case EK_OP_TRUNC: return SEL(DOP_TRUNC_F32, DOP_TRUNC_F64, DOP_LOAD_32, DOP_LOAD_32, DOP_LOAD_64, DOP_LOAD_64);
         case EK_OP_NOT:   return vt == EK_BOOL ? DOP_NOT_B : SEL(DOP_NOT_32, DOP_NOT_64, DOP_NOT_32, DOP_NOT_32, DOP_NOT_64, DOP_NOT_64);
         case EK_OP_POPC:  return SEL(-1, -1, DOP_POPC_32, DOP_POPC_32, DOP_POPC_64, DOP_POPC_64);
         case EK_OP_CLZ:   return SEL(-1, -1, DOP_CLZ_32, DOP_CLZ_32, DOP_CLZ_64, DOP_CLZ_64);
@@ -148,7 +148,7 @@ int pick_op(ek_op op, ek_type vt, ek_type at /* operand type */) {
         case EK_OP_MUL_NZ: return SEL(DOP_MULNZ_F32, DOP_MULNZ_F64, -1, -1, -1, -1);
         case EK_OP_FMA:   return SEL(DOP_FMA_F32, DOP_FMA_F64, DOP_MAD_I32, DOP_MAD_I32, DOP_MAD_I64, DOP_MAD_I64);
         case EK_OP_FMA_NZ: return SEL(DOP_FMANZ_F32, DOP_FMANZ_F64, -1, -1, -1, -1);
-        case EK_OP_SELECT: return SEL(DOP_SELECT_32, DOP_SELECT_64, DOP_SELECT_32, DOP_SELECT_32, DOP_SELECT_64, DOP_SELECT_64);
+        case EK_OP_SELECT: return SEL(DOP_SEL_M_32, DOP_SEL_M_64, DOP_SEL_M_32, DOP_SEL_M_32, DOP_SEL_M_64, DOP_SEL_M_64);
         default: return -1;
     }
 }
@@ -158,12 +158,12 @@ int pick_cvt(ek_type src, ek_type dst) {
     Cls s = cls_of(src), d = cls_of(dst);
     if (s == C_BAD || d == C_BAD) return -1;
     static const int tab[6][6] = {
-        /* from F32 */ { DOP_MOV_32, DOP_CVT_F32_F64, DOP_CVT_F32_I32, DOP_CVT_F32_U32, DOP_CVT_F32_I64, DOP_CVT_F32_U64 },
-        /* from F64 */ { DOP_CVT_F64_F32, DOP_MOV_64, DOP_CVT_F64_I32, DOP_CVT_F64_U32, DOP_CVT_F64_I64, DOP_CVT_F64_U64 },
-        /* from I32 */ { DOP_CVT_I32_F32, DOP_CVT_I32_F64, DOP_MOV_32, DOP_MOV_32, DOP_CVT_I32_I64, DOP_CVT_I32_I64 },
-        /* from U32 */ { DOP_CVT_U32_F32, DOP_CVT_U32_F64, DOP_MOV_32, DOP_MOV_32, DOP_CVT_U32_U64, DOP_CVT_U32_U64 },
-        /* from I64 */ { DOP_CVT_I64_F32, DOP_CVT_I64_F64, DOP_CVT_64_32, DOP_CVT_64_32, DOP_MOV_64, DOP_MOV_64 },
-        /* from U64 */ { DOP_CVT_U64_F32, DOP_CVT_U64_F64, DOP_CVT_64_32, DOP_CVT_64_32, DOP_MOV_64, DOP_MOV_64 } };
+        /* from F32 */ { DOP_LOAD_32, DOP_CVT_F32_F64, DOP_CVT_F32_I32, DOP_CVT_F32_U32, DOP_CVT_F32_I64, DOP_CVT_F32_U64 },
+        /* from F64 */ { DOP_CVT_F64_F32, DOP_LOAD_64, DOP_CVT_F64_I32, DOP_CVT_F64_U32, DOP_CVT_F64_I64, DOP_CVT_F64_U64 },
+        /* from I32 */ { DOP_CVT_I32_F32, DOP_CVT_I32_F64, DOP_LOAD_32, DOP_LOAD_32, DOP_CVT_I32_I64, DOP_CVT_I32_I64 },
+        /* from U32 */ { DOP_CVT_U32_F32, DOP_CVT_U32_F64, DOP_LOAD_32, DOP_LOAD_32, DOP_CVT_U32_U64, DOP_CVT_U32_U64 },
+        /* from I64 */ { DOP_CVT_I64_F32, DOP_CVT_I64_F64, DOP_CVT_64_32, DOP_CVT_64_32, DOP_LOAD_64, DOP_LOAD_64 },
+        /* from U64 */ { DOP_CVT_U64_F32, DOP_CVT_U64_F64, DOP_CVT_64_32, DOP_CVT_64_32, DOP_LOAD_64, DOP_LOAD_64 } };
     return tab[s][d];
 }
 
@@ -189,6 +189,18 @@ uint64_t red_identity(int kind, int cls) {
 }
 
 /* ------------------------------------------------------------------ assembler */
+/* operand positions of `op` that may be served from the accumulator (bit p = dep[p]) */
+uint32_t acc_positions(const EkVariable &v) {
+    ek_op op = v.op;
+    if (op == EK_OP_LITERAL || op == EK_OP_INDEX) return 0;
+    if (op >= EK_OP_MOV && op <= EK_OP_CTZ) return 1;
+    if (op >= EK_OP_ADD && op <= EK_OP_MUL_NZ) return 3;
+    if (op == EK_OP_FMA || op == EK_OP_SELECT || op == EK_OP_FMA_NZ) return 7;
+    if (op == EK_OP_GATHER || op == EK_OP_SCATTER || op == EK_OP_SCATTER_ADD) return 2;   /* the index */
+    if (op >= EK_OP_HSUM && op <= EK_OP_COUNT) return 1;
+    return 0;
+}
+
 struct Assembler {
     EkContext &ctx;
     const Group &g;
@@ -200,6 +212,7 @@ struct Assembler {
     std::unordered_map<uint32_t, uint32_t> last_use;   /* var -> sched position of last consumer */
     std::unordered_map<uint32_t, uint32_t> epos;       /* var -> emit index */
     std::unordered_map<uint32_t, uint32_t> last_epos;  /* var -> max emit index among consumers */
+    std::unordered_set<uint32_t> force_slot;           /* next consumer cannot take it from the accumulator */
     std::unordered_map<uint64_t, uint32_t> lit32, lit64;
     std::vector<uint8_t> slot_used;
     std::unordered_map<uint32_t, uint32_t> red_acc;    /* reduce var -> accumulator slot */
@@ -244,24 +257,23 @@ struct Assembler {
             if (ok) { for (uint32_t k = 0; k < n; ++k) slot_used[s + k] = 1; return s; }
         }
         uint32_t s = (uint32_t) slot_used.size();
-        /* keep pairs contiguous: if the last slot is free and n == 2, extend from it */
         if (n == 2 && s > 0 && !slot_used[s - 1]) { slot_used[s - 1] = 1; slot_used.push_back(1); return s - 1; }
         for (uint32_t k = 0; k < n; ++k) slot_used.push_back(1);
         return s;
     }
     void free_slots(uint32_t s, uint32_t n) { for (uint32_t k = 0; k < n; ++k) slot_used[s + k] = 0; }
 
-    /* uniform codes are encoded with a marker and rebased in finish():
-       literal word i -> 0x8000 | i ; argument word j -> 0x8000 | 0x2000 | j (rebased by n_lit) */
+    /* uniform codes carry a marker that is rebased in finish():
+       literal word i -> 0x8000 | i ; argument word j -> 0x8000 | 0x2000 | j ; scalar word -> 0x8000 | 0x1000 | k */
     static uint16_t uni_lit(uint32_t i) { return (uint16_t) (0x8000u | i); }
     static uint16_t uni_arg(uint32_t j) { return (uint16_t) (0x8000u | 0x2000u | j); }
-    static uint16_t staged_code(uint32_t unit) { return (uint16_t) (0x4000u | unit); }
+    static uint16_t staged_code(uint32_t unit) { return (uint16_t) (EK_OPND_STAGED | unit); }
 
     bool fail(const std::string &m) { if (out.error.empty()) out.error = m; return false; }
     bool fail_resource(const std::string &m) { out.resource_error = true; return fail(m); }
 
+    /* shared-memory operand code of a value that is NOT taken from the accumulator */
     uint16_t operand(uint32_t v) {
-        if (v == acc_var) return EK_OPND_ACC;
         auto it = loc.find(v);
         if (it == loc.end()) { fail("internal: operand " + std::to_string(v) + " has no location"); return EK_OPND_NONE; }
         switch (it->second.kind) {
@@ -282,30 +294,46 @@ struct Assembler {
         }
     }
 
-    EkInstr mk(int op, uint16_t a = EK_OPND_NONE, uint16_t b = EK_OPND_NONE, uint16_t c = EK_OPND_NONE,
-               uint32_t nargs = 0, uint32_t imm = 0) {
+    EkInstr mk(int op, uint32_t imm = 0) {
         EkInstr in;
-        in.op = (uint16_t) op; in.dst = 0; in.a = a; in.b = b; in.c = c;
-        in.flags = EKF_NARG(nargs); in.imm = imm;
+        in.op = (uint16_t) op; in.flags = 0; in.dst = 0; in.b = EK_OPND_NONE; in.c = EK_OPND_NONE; in.pad = 0; in.imm = imm;
         return in;
+    }
+    void set_b(EkInstr &in, uint32_t v) { in.b = operand(v); in.flags |= EKF_HAS_B; if (ek_is_64(var(v).type)) in.flags |= EKF_B64; }
+    void set_c(EkInstr &in, uint32_t v) { in.c = operand(v); in.flags |= EKF_HAS_C; if (ek_is_64(var(v).type)) in.flags |= EKF_C64; }
+    void set_b_code(EkInstr &in, uint16_t code, bool is64) { in.b = code; in.flags |= EKF_HAS_B; if (is64) in.flags |= EKF_B64; }
+    void set_c_code(EkInstr &in, uint16_t code, bool is64) { in.c = code; in.flags |= EKF_HAS_C; if (is64) in.flags |= EKF_C64; }
+
+    /* make `v` the accumulator content (emits a LOAD when it is not already there) */
+    void ensure_acc(uint32_t v) {
+        if (acc_var == v) return;
+        bool is64 = ek_is_64(var(v).type);
+        EkInstr in = mk(is64 ? DOP_LOAD_64 : DOP_LOAD_32);
+        set_b(in, v);
+        out.body.push_back(in);
+        acc_var = v;
     }
 
     /* give the value of `v` (just produced into the accumulator by `in`) a home */
-    void place_result(EkInstr &in, uint32_t v, bool produces) {
-        if (!produces) return;
+    void place_result(EkInstr &in, uint32_t v) {
         const EkVariable &vv = var(v);
         bool is64 = ek_is_64(vv.type);
-        if (is64) in.flags |= EKF_R64;
         auto le = last_epos.find(v);
-        bool needs_slot = le != last_epos.end() && le->second > cur_e + 1;
+        bool needs_slot = (le != last_epos.end() && le->second > cur_e + 1) || force_slot.count(v);
         if (needs_slot) {
             uint32_t s = alloc_slots(is64 ? 2 : 1);
-            in.flags |= EKF_ST; in.dst = (uint16_t) s;
+            in.flags |= EKF_ST | (is64 ? EKF_R64 : 0); in.dst = (uint16_t) s;
             loc[v] = { Loc::SLOT, (uint16_t) s };
         } else {
             loc[v] = { Loc::PENDING, 0 };
         }
     }
+
+    bool lit_emits(uint32_t idx) const {
+        const EkVariable &v = var(idx);
+        return v.op == EK_OP_LITERAL && v.size == g.size && ((v.ref_ext > 0 && !v.side_effect) || forced.count(idx));
+    }
+    bool boundary_input(uint32_t idx) const { return g.boundary.count(idx) != 0; }
 
     bool run() {
         /* ---- pass 0: wide inputs beyond the staging budget are loaded directly (ld.global) ---- */
@@ -321,9 +349,10 @@ struct Assembler {
             }
         }
 
-        /* ---- pass 1: classify inputs, count uses ---- */
+        /* ---- pass 1: emit indices, last uses, accumulator compatibility ---- */
         uint32_t e = 0;
         std::vector<uint32_t> emits(g.sched.size(), 0);
+        uint32_t prev_emitted = 0;
         for (size_t i = 0; i < g.sched.size(); ++i) {
             uint32_t idx = g.sched[i];
             const EkVariable &v = var(idx);
@@ -334,12 +363,20 @@ struct Assembler {
             else emitting = true;
             if (emitting) {
                 ++e;
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t d = v.dep[k];
-                    if (d < EK_REG_RESERVED) continue;
-                    last_use[d] = (uint32_t) i;
-                    last_epos[d] = e;
+                bool computes = !is_input && v.op != EK_OP_LITERAL;
+                if (computes) {
+                    uint32_t accp = acc_positions(v);
+                    bool prev_ok = false, prev_used = false;
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t d = v.dep[k];
+                        if (d < EK_REG_RESERVED) continue;
+                        last_use[d] = (uint32_t) i;
+                        last_epos[d] = e;
+                        if (d == prev_emitted) { prev_used = true; if (k < 3 && (accp >> k) & 1u) prev_ok = true; }
+                    }
+                    if (prev_used && !prev_ok) force_slot.insert(prev_emitted);
                 }
+                prev_emitted = idx;
             }
             emits[i] = e;
             epos[idx] = e;
@@ -367,7 +404,6 @@ struct Assembler {
                     out.bytes_in += (uint64_t) v.size * es;       /* emitted as LDG in pass 2 */
                 } else {
                     if (v.size != g.size) return fail("encountered arrays of incompatible size");
-                    if (out.staged.size() >= EK_MAX_STAGED) return fail_resource("too many input arrays in one kernel (limit " + std::to_string(EK_MAX_STAGED) + "); call cuda_eval() earlier");
                     uint32_t units = es == 8 ? 2 : 1;
                     out.staged.push_back({ idx, (uint16_t) unit, (uint8_t) es });
                     loc[idx] = { Loc::STAGED, (uint16_t) unit };
@@ -403,7 +439,8 @@ struct Assembler {
                 case EK_FLOAT16: return fail("Float16 arrays are not supported");
                 default: op = DOP_LD_64; break;
             }
-            EkInstr in = mk(op, staged_code(loc[idx].idx));
+            EkInstr in = mk(op);
+            in.b = staged_code(loc[idx].idx);       /* raw staged code; no generic fetch (EKF_HAS_B clear) */
             bool is64 = ek_is_64(v.type);
             uint32_t s = alloc_slots(is64 ? 2 : 1);
             in.flags |= EKF_ST | (is64 ? EKF_R64 : 0); in.dst = (uint16_t) s;
@@ -430,9 +467,9 @@ struct Assembler {
                     default: op = DOP_LDG_64; break;
                 }
                 uint32_t pa = arg_ptr(idx, false);
-                EkInstr in = mk(op, EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, uni_arg(pa) & 0x7fffu);
-                in.flags |= 0x4000u;
-                place_result(in, idx, true);
+                EkInstr in = mk(op, uni_arg(pa) & 0x7fffu);
+                in.pad = 1;                    /* marker: imm holds an argument-word index to rebase */
+                place_result(in, idx);
                 out.body.push_back(in);
                 acc_var = idx;
                 continue;
@@ -445,44 +482,20 @@ struct Assembler {
         return finish();
     }
 
-    /* literals are immediates; they only become instructions when they must be materialised
-       (externally referenced root of this sweep's size, e.g. `Float c = 2.f; c.eval()`) */
-    bool lit_emits(uint32_t idx) const {
-        const EkVariable &v = var(idx);
-        return v.op == EK_OP_LITERAL && v.size == g.size && ((v.ref_ext > 0 && !v.side_effect) || forced.count(idx));
-    }
-
-    /* a variable that is computed by an EARLIER launch of this eval (reduction result or forced
-       scalar) and is therefore an input here */
-    bool boundary_input(uint32_t idx) const {
-        if (var(idx).data != nullptr) return false;
-        return g.boundary.count(idx) != 0;
-    }
-
     bool emit_var(uint32_t idx, uint32_t pos) {
         const EkVariable &v = var(idx);
         ek_op op = v.op;
         ek_type t = v.type;
         bool is64 = ek_is_64(t);
         out.n_arith++;
+        uint32_t d0 = v.dep[0], d1 = v.dep[1], d2 = v.dep[2], d3 = v.dep[3];
 
-        auto opflags = [&](EkInstr &in, uint32_t a, uint32_t b, uint32_t c) {
-            if (a && ek_is_64(var(a).type)) in.flags |= EKF_A64;
-            if (b && ek_is_64(var(b).type)) in.flags |= EKF_B64;
-            if (c && ek_is_64(var(c).type)) in.flags |= EKF_C64;
-        };
-        auto after = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-            if (a) release(a, pos);
-            if (b) release(b, pos);
-            if (c) release(c, pos);
-            if (d) release(d, pos);
-        };
-
+        auto after = [&]() { if (d0) release(d0, pos); if (d1) release(d1, pos); if (d2) release(d2, pos); if (d3) release(d3, pos); };
         if (t == EK_FLOAT16) return fail("Float16 arithmetic is not supported");
 
+        /* ---------------- reductions ---------------- */
         if (is_reduce(op)) {
-            uint32_t x = v.dep[0];
-            ek_type xt = var(x).type;
+            ek_type xt = var(d0).type;
             int kind, cls = red_class(xt);
             switch (op) {
                 case EK_OP_HSUM: kind = EK_RED_SUM; break;
@@ -498,36 +511,45 @@ struct Assembler {
             uint32_t ridx = out.n_red++;
             uint32_t acc = red_acc[idx];                 /* reserved in run(); never freed */
             uint64_t ident = red_identity(kind, cls);
-            EkInstr ini = mk(w64 ? DOP_MOV_64 : DOP_MOV_32, w64 ? uni_lit(lit_pair(ident)) : uni_lit(lit_word((uint32_t) ident)),
-                             EK_OPND_NONE, EK_OPND_NONE, 1);
-            ini.flags |= EKF_ST | (w64 ? (EKF_R64 | EKF_A64) : 0); ini.dst = (uint16_t) acc;
+            EkInstr ini = mk(w64 ? DOP_LOAD_64 : DOP_LOAD_32);
+            set_b_code(ini, w64 ? uni_lit(lit_pair(ident)) : uni_lit(lit_word((uint32_t) ident)), w64);
+            ini.flags |= EKF_ST | (w64 ? EKF_R64 : 0); ini.dst = (uint16_t) acc;
             out.init.push_back(ini);
-            EkInstr in = mk(DOP_RACC, operand(x), EK_OPND_NONE, EK_OPND_NONE, 1, (uint32_t) kind | ((uint32_t) cls << 8));
-            if (w64) in.flags |= EKF_A64;
+            ensure_acc(d0);
+            EkInstr in = mk(DOP_RACC, (uint32_t) kind | ((uint32_t) cls << 8));
             in.dst = (uint16_t) acc;
             out.body.push_back(in);
             uint32_t pa = arg_ptr(idx, true);
             out.outputs.push_back({ idx, pa, 8 });
-            EkInstr fi = mk(DOP_RFIN, (uint16_t) acc, EK_OPND_NONE, EK_OPND_NONE, 1,
-                            (uint32_t) kind | ((uint32_t) cls << 8) | (ridx << 16));
-            if (w64) fi.flags |= EKF_A64;
-            fi.dst = uni_arg(pa) & 0x7fffu;      /* plain uniform index (rebased in finish) */
+            EkInstr fi = mk(DOP_RFIN, (uint32_t) kind | ((uint32_t) cls << 8) | (ridx << 16));
+            set_b_code(fi, (uint16_t) acc, w64);
+            fi.dst = (uint16_t) pa; fi.pad = 2;          /* marker: dst holds an argument-word index to rebase */
             out.fini.push_back(fi);
-            after(x, 0, 0, 0);
+            after();
             return out.error.empty();
         }
 
-        EkInstr in;
+        EkInstr in = mk(DOP_NOP);
         bool produces = true;
-        uint32_t d0 = v.dep[0], d1 = v.dep[1], d2 = v.dep[2], d3 = v.dep[3];
+
+        /* operand that is currently in the accumulator among the positions the op accepts */
+        auto acc_at = [&](uint32_t a, uint32_t b, uint32_t c) -> int {
+            if (a && a == acc_var) return 0;
+            if (b && b == acc_var) return 1;
+            if (c && c == acc_var) return 2;
+            return -1;
+        };
+        /* fetch operand v into B / C, or alias the accumulator when it is the same value */
+        auto put_b = [&](EkInstr &ins, uint32_t vv) { if (vv == acc_var) { ensure_slot_or_alias(ins, vv, true); } else set_b(ins, vv); };
+        auto put_c = [&](EkInstr &ins, uint32_t vv) { if (vv == acc_var) { ensure_slot_or_alias(ins, vv, false); } else set_c(ins, vv); };
 
         switch (op) {
             case EK_OP_INDEX:
                 in = mk(DOP_INDEX);
                 break;
             case EK_OP_LITERAL:
-                in = mk(is64 ? DOP_MOV_64 : DOP_MOV_32, loc[idx].idx, EK_OPND_NONE, EK_OPND_NONE, 1);
-                if (is64) in.flags |= EKF_A64;
+                in = mk(is64 ? DOP_LOAD_64 : DOP_LOAD_32);
+                set_b_code(in, loc[idx].idx, is64);
                 break;
             case EK_OP_CVT: case EK_OP_FLOOR2INT: case EK_OP_CEIL2INT: {
                 ek_type st = var(d0).type;
@@ -538,13 +560,13 @@ struct Assembler {
                 } else dop = pick_cvt(st, t);
                 if (dop < 0) return fail("unsupported conversion");
                 uint32_t mode = op == EK_OP_FLOOR2INT ? EK_RM : op == EK_OP_CEIL2INT ? EK_RP : EK_RZ;
-                in = mk(dop, operand(d0), EK_OPND_NONE, EK_OPND_NONE, 1, mode);
-                opflags(in, d0, 0, 0);
+                ensure_acc(d0);
+                in = mk(dop == DOP_LOAD_32 || dop == DOP_LOAD_64 ? DOP_NOP : dop, mode);
             } break;
             case EK_OP_BITCAST: {
                 if (ek_type_size(var(d0).type) != ek_type_size(t)) return fail("bitcast between types of different size");
-                in = mk(is64 ? DOP_MOV_64 : DOP_MOV_32, operand(d0), EK_OPND_NONE, EK_OPND_NONE, 1);
-                opflags(in, d0, 0, 0);
+                ensure_acc(d0);
+                in = mk(DOP_NOP);
             } break;
             case EK_OP_GATHER: {
                 const EkVariable &pv = var(d0);
@@ -568,17 +590,20 @@ struct Assembler {
                     if (tv.data == pv.data && tv.size <= 4096 && ek_type_size(tv.type) == 4) smem_table = true;
                 }
                 uint32_t pa = loc[d0].idx;   /* uniform code of the pointer words */
+                ensure_acc(d1);
                 if (smem_table) {
                     uint32_t count = (uint32_t) var(v.extra_dep).size;
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(1); out.argw.push_back(pa);
                     out.extra_bytes += (count * 4 + 15) & ~15u;
-                    out.init.push_back(mk(DOP_SMEM_LOAD_TABLE, EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, 0x80000000u | di));
-                    in = mk(DOP_GATHER_32_SMEM, operand(d1), operand(d2), EK_OPND_NONE, 2, 0x80000000u | di);
+                    EkInstr li = mk(DOP_SMEM_LOAD_TABLE, di); li.pad = 1;
+                    out.init.push_back(li);
+                    in = mk(DOP_GATHER_32_SMEM, di); in.pad = 1;
                 } else {
-                    in = mk(dop, operand(d1), operand(d2), EK_OPND_NONE, 2, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
-                    in.flags |= 0x8000u;     /* marker: imm low 16 bits hold a uniform code to rebase */
+                    in = mk(dop, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
+                    in.pad = 3;              /* marker: imm low 16 bits hold a uniform code to rebase */
                 }
+                put_b(in, d2);
                 if (ek_is_64(it)) in.flags |= EKF_A64;
             } break;
             case EK_OP_SCATTER: case EK_OP_SCATTER_ADD: {
@@ -606,55 +631,104 @@ struct Assembler {
                     }
                 }
                 uint32_t pa = loc[d0].idx;
+                ensure_acc(d1);
                 if (smem_bins) {
                     uint32_t count = (uint32_t) var(v.extra_dep).size;
                     uint32_t copies = std::max(1u, std::min(16u, 4096u / count));
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(copies); out.argw.push_back(pa);
                     out.extra_bytes += (count * copies * 4 + 15) & ~15u;
-                    out.init.push_back(mk(DOP_SMEM_ZERO, EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, 0x80000000u | di));
-                    out.fini.push_back(mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SMEM_FLUSH_ADD_F32 : DOP_SMEM_FLUSH_ADD_I32,
-                                          EK_OPND_NONE, EK_OPND_NONE, EK_OPND_NONE, 0, 0x80000000u | di));
-                    in = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SCATTER_ADD_F32_SMEM : DOP_SCATTER_ADD_I32_SMEM,
-                            operand(d1), operand(d3), operand(d2), 3, 0x80000000u | di);
+                    EkInstr zi = mk(DOP_SMEM_ZERO, di); zi.pad = 1; out.init.push_back(zi);
+                    EkInstr fl = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SMEM_FLUSH_ADD_F32 : DOP_SMEM_FLUSH_ADD_I32, di); fl.pad = 1;
+                    out.fini.push_back(fl);
+                    in = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SCATTER_ADD_F32_SMEM : DOP_SCATTER_ADD_I32_SMEM, di); in.pad = 1;
                 } else {
-                    in = mk(dop, operand(d1), operand(d3), operand(d2), 3, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
-                    in.flags |= 0x8000u;
+                    in = mk(dop, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
+                    in.pad = 3;
                 }
+                put_b(in, d3);
+                put_c(in, d2);
                 if (ek_is_64(it)) in.flags |= EKF_A64;
-                if (ek_is_64(vt)) in.flags |= EKF_B64;
                 produces = false;
+            } break;
+            case EK_OP_SELECT: {
+                int p = acc_at(d0, d1, d2);
+                if (p < 0) { ensure_acc(d0); p = 0; }
+                int dop = p == 0 ? (is64 ? DOP_SEL_M_64 : DOP_SEL_M_32) : p == 1 ? (is64 ? DOP_SEL_T_64 : DOP_SEL_T_32)
+                                                                                 : (is64 ? DOP_SEL_F_64 : DOP_SEL_F_32);
+                in = mk(dop);
+                if (p == 0) { put_b(in, d1); put_c(in, d2); }
+                else if (p == 1) { put_b(in, d0); put_c(in, d2); }
+                else { put_b(in, d0); put_c(in, d1); }
+            } break;
+            case EK_OP_FMA: case EK_OP_FMA_NZ: {
+                int p = acc_at(d0, d1, d2);
+                if (p < 0) { ensure_acc(d0); p = 0; }
+                Cls c = cls_of(t);
+                int base, basec;
+                if (op == EK_OP_FMA) {
+                    base = SEL(DOP_FMA_F32, DOP_FMA_F64, DOP_MAD_I32, DOP_MAD_I32, DOP_MAD_I64, DOP_MAD_I64);
+                    basec = SEL(DOP_FMAC_F32, DOP_FMAC_F64, DOP_MADC_I32, DOP_MADC_I32, DOP_MADC_I64, DOP_MADC_I64);
+                } else {
+                    if (c != C_F32 && c != C_F64) return fail("fma_nz: floating point only");
+                    base = c == C_F32 ? DOP_FMANZ_F32 : DOP_FMANZ_F64;
+                    basec = c == C_F32 ? DOP_FMANZC_F32 : DOP_FMANZC_F64;
+                }
+                in = mk(p == 2 ? basec : base);
+                if (p == 0) { put_b(in, d1); put_c(in, d2); }
+                else if (p == 1) { put_b(in, d0); put_c(in, d2); }
+                else { put_b(in, d0); put_c(in, d1); }
             } break;
             case EK_OP_AND: case EK_OP_OR: {
                 ek_type bt = var(d1).type;
                 if (t != EK_BOOL && bt == EK_BOOL) {
-                    /* value & mask / value | mask (cuda.h:545-572): select forms */
-                    uint16_t zero = is64 ? uni_lit(lit_pair(op == EK_OP_AND ? 0ull : ~0ull))
-                                         : uni_lit(lit_word(op == EK_OP_AND ? 0u : 0xffffffffu));
-                    if (op == EK_OP_AND) in = mk(is64 ? DOP_SELECT_64 : DOP_SELECT_32, operand(d1), operand(d0), zero, 3);
-                    else                 in = mk(is64 ? DOP_SELECT_64 : DOP_SELECT_32, operand(d1), zero, operand(d0), 3);
-                    if (is64) in.flags |= EKF_B64 | EKF_C64;
+                    /* value & mask = select(mask, value, 0); value | mask = select(mask, ~0, value) (cuda.h:545-572) */
+                    uint16_t k = is64 ? uni_lit(lit_pair(op == EK_OP_AND ? 0ull : ~0ull))
+                                      : uni_lit(lit_word(op == EK_OP_AND ? 0u : 0xffffffffu));
+                    int p = acc_at(d0, d1, 0);
+                    if (p < 0) { ensure_acc(d0); p = 0; }
+                    if (op == EK_OP_AND) {
+                        if (p == 0) { in = mk(is64 ? DOP_SEL_T_64 : DOP_SEL_T_32); put_b(in, d1); set_c_code(in, k, is64); }
+                        else        { in = mk(is64 ? DOP_SEL_M_64 : DOP_SEL_M_32); put_b(in, d0); set_c_code(in, k, is64); }
+                    } else {
+                        if (p == 0) { in = mk(is64 ? DOP_SEL_F_64 : DOP_SEL_F_32); put_b(in, d1); set_c_code(in, k, is64); }
+                        else        { in = mk(is64 ? DOP_SEL_M_64 : DOP_SEL_M_32); set_b_code(in, k, is64); put_c(in, d0); }
+                    }
                     break;
                 }
             }   /* fall through */
             default: {
-                int arity = 0;
-                uint32_t deps[3] = { d0, d1, d2 };
-                if (op >= EK_OP_MOV && op <= EK_OP_CTZ) arity = 1;
-                else if (op >= EK_OP_ADD && op <= EK_OP_MUL_NZ) arity = 2;
-                else if (op == EK_OP_FMA || op == EK_OP_SELECT || op == EK_OP_FMA_NZ) arity = 3;
-                else return fail(std::string("unsupported op ") + ek_op_name(op));
-                ek_type at = var(d0).type;
-                int dop = pick_op(op, t, at);
-                if (dop < 0) return fail(std::string("op ") + ek_op_name(op) + " not supported for type " + ek_type_name(op >= EK_OP_GT && op <= EK_OP_NE ? at : t));
-                in = mk(dop, operand(deps[0]), arity > 1 ? operand(deps[1]) : EK_OPND_NONE,
-                        arity > 2 ? operand(deps[2]) : EK_OPND_NONE, arity);
-                opflags(in, deps[0], arity > 1 ? deps[1] : 0, arity > 2 ? deps[2] : 0);
-                /* 64-bit shifts take a 32-bit count (cuda.h:503-505) */
-                if ((op == EK_OP_SHL || op == EK_OP_SHR) && is64 && ek_is_64(var(d1).type)) {
-                    /* count operand arrives as 64-bit: only its low plane is read */
-                    in.flags &= ~EKF_B64;
-                }
+                if (op >= EK_OP_MOV && op <= EK_OP_CTZ) {                 /* unary */
+                    ek_type at = var(d0).type;
+                    int dop = pick_op(op, t, at);
+                    if (dop < 0) return fail(std::string("op ") + ek_op_name(op) + " not supported for type " + ek_type_name(t));
+                    ensure_acc(d0);
+                    in = mk(dop == DOP_LOAD_32 || dop == DOP_LOAD_64 ? DOP_NOP : dop);
+                } else if (op >= EK_OP_ADD && op <= EK_OP_MUL_NZ) {       /* binary */
+                    ek_type at = var(d0).type;
+                    int p = acc_at(d0, d1, 0);
+                    if (p < 0) { ensure_acc(d0); p = 0; }
+                    ek_op eop = op;
+                    bool reversed = false;
+                    if (p == 1) {
+                        switch (op) {
+                            case EK_OP_GT: eop = EK_OP_LT; break;
+                            case EK_OP_GE: eop = EK_OP_LE; break;
+                            case EK_OP_LT: eop = EK_OP_GT; break;
+                            case EK_OP_LE: eop = EK_OP_GE; break;
+                            case EK_OP_SUB: case EK_OP_DIV: case EK_OP_MOD: case EK_OP_SHL: case EK_OP_SHR: reversed = true; break;
+                            case EK_OP_MIN: case EK_OP_MAX: reversed = ek_is_float(t); break;
+                            default: break;       /* commutative */
+                        }
+                    }
+                    int dop = pick_op(eop, t, at);
+                    if (dop < 0) return fail(std::string("op ") + ek_op_name(op) + " not supported for type " + ek_type_name(op >= EK_OP_GT && op <= EK_OP_NE ? at : t));
+                    if (reversed) { dop = reversed_op(dop); if (dop < 0) return fail("internal: no reversed variant"); }
+                    in = mk(dop);
+                    put_b(in, p == 0 ? d1 : d0);
+                    /* 64-bit shifts take a 32-bit count (cuda.h:503-505): only the low plane of the count is read */
+                    if ((op == EK_OP_SHL || op == EK_OP_SHR) && is64 && !reversed) in.flags &= ~EKF_B64;
+                } else return fail(std::string("unsupported op ") + ek_op_name(op));
             } break;
         }
 
@@ -664,18 +738,17 @@ struct Assembler {
         if (arith_narrow) nop = norm_op(t);
 
         if (nop >= 0 && produces) {
-            if (is64) in.flags |= EKF_R64;
             out.body.push_back(in);
-            acc_var = 0;
-            EkInstr nn = mk(nop, EK_OPND_ACC, EK_OPND_NONE, EK_OPND_NONE, 1);
-            after(d0, d1, d2, d3);
-            place_result(nn, idx, true);
+            EkInstr nn = mk(nop);
+            after();
+            place_result(nn, idx);
             out.body.push_back(nn);
             acc_var = idx;
         } else {
-            after(d0, d1, d2, d3);
-            place_result(in, idx, produces);
-            out.body.push_back(in);
+            after();
+            if (produces) place_result(in, idx);
+            /* a pure rename (NOP) that needs no slot emits nothing at all */
+            if (!(in.op == DOP_NOP && !(in.flags & EKF_ST))) out.body.push_back(in);
             if (produces) acc_var = idx;
         }
 
@@ -687,14 +760,47 @@ struct Assembler {
                 uint32_t pa = arg_ptr(idx, true);
                 out.outputs.push_back({ idx, pa, std::max<size_t>(v.size * es, 8) });
                 int sop = es == 1 ? DOP_ST_8 : es == 2 ? DOP_ST_16 : es == 4 ? DOP_ST_32 : DOP_ST_64;
-                EkInstr st = mk(sop, EK_OPND_ACC, EK_OPND_NONE, EK_OPND_NONE, 1, uni_arg(pa) & 0x7fffu);
-                if (es == 8) st.flags |= EKF_A64 | EKF_R64;
-                st.flags |= 0x4000u;      /* marker: imm holds a uniform index to rebase */
+                EkInstr st = mk(sop, pa);
+                st.pad = 1;
                 out.body.push_back(st);
                 out.bytes_out += (uint64_t) v.size * es;
             }
         }
         return out.error.empty();
+    }
+
+    /* the value in the accumulator is also needed as B / C of the same instruction (e.g. t*t):
+       it must have a slot (guaranteed by force_slot in pass 1 when last use > e+1) -- otherwise spill
+       it to a scratch slot first */
+    void ensure_slot_or_alias(EkInstr &ins, uint32_t vv, bool as_b) {
+        auto l = loc.find(vv);
+        if (l == loc.end() || l->second.kind != Loc::SLOT) {
+            bool is64 = ek_is_64(var(vv).type);
+            uint32_t s = alloc_slots(is64 ? 2 : 1);
+            EkInstr sp = mk(DOP_NOP);
+            sp.flags |= EKF_ST | (is64 ? EKF_R64 : 0); sp.dst = (uint16_t) s;
+            out.body.push_back(sp);
+            loc[vv] = { Loc::SLOT, (uint16_t) s };
+            scratch.push_back({ s, is64 ? 2u : 1u });
+        }
+        if (as_b) set_b(ins, vv); else set_c(ins, vv);
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> scratch;
+
+    static int reversed_op(int dop) {
+        switch (dop) {
+            case DOP_SUB_F32: return DOP_SUBR_F32; case DOP_DIV_F32: return DOP_DIVR_F32;
+            case DOP_MIN_F32: return DOP_MINR_F32; case DOP_MAX_F32: return DOP_MAXR_F32;
+            case DOP_SUB_F64: return DOP_SUBR_F64; case DOP_DIV_F64: return DOP_DIVR_F64;
+            case DOP_MIN_F64: return DOP_MINR_F64; case DOP_MAX_F64: return DOP_MAXR_F64;
+            case DOP_SUB_I32: return DOP_SUBR_I32; case DOP_DIV_I32: return DOP_DIVR_I32; case DOP_DIV_U32: return DOP_DIVR_U32;
+            case DOP_MOD_I32: return DOP_MODR_I32; case DOP_MOD_U32: return DOP_MODR_U32;
+            case DOP_SHL_32: return DOP_SHLR_32; case DOP_SHR_I32: return DOP_SHRR_I32; case DOP_SHR_U32: return DOP_SHRR_U32;
+            case DOP_SUB_I64: return DOP_SUBR_I64; case DOP_DIV_I64: return DOP_DIVR_I64; case DOP_DIV_U64: return DOP_DIVR_U64;
+            case DOP_MOD_I64: return DOP_MODR_I64; case DOP_MOD_U64: return DOP_MODR_U64;
+            case DOP_SHL_64: return DOP_SHLR_64; case DOP_SHR_I64: return DOP_SHRR_I64; case DOP_SHR_U64: return DOP_SHRR_U64;
+            default: return -1;
+        }
     }
 
     /* rebase uniform indices now that the literal count is known:
@@ -705,41 +811,33 @@ struct Assembler {
         if (n_arg > EK_MAX_ARGW) return fail_resource("too many kernel arguments; call cuda_eval() earlier");
         if (n_lit + n_arg + 2 * out.scalars.size() >= 0x1000u) return fail_resource("uniform pool overflow");
         out.n_tmp = (uint32_t) slot_used.size();
+        if (out.n_tmp >= 0x3fffu) return fail_resource("too many live values");
         auto rebase_code = [&](uint16_t code) -> uint16_t {
-            if (code == EK_OPND_NONE || code == EK_OPND_ACC) return code;
+            if (code == EK_OPND_NONE) return code;
             if (code & 0x8000u) {
                 uint32_t i = code & 0x0fffu;
                 if (code & 0x2000u) return (uint16_t) (0x8000u | (n_lit + i));
                 if (code & 0x1000u) return (uint16_t) (0x8000u | (n_lit + n_arg + i));
                 return (uint16_t) (0x8000u | i);
             }
-            if ((code & 0xC000u) == 0x4000u) return (uint16_t) (out.n_tmp + (code & 0x3fffu));
             return code;
         };
         auto fix = [&](std::vector<EkInstr> &v) {
             for (EkInstr &in : v) {
-                in.a = rebase_code(in.a); in.b = rebase_code(in.b); in.c = rebase_code(in.c);
-                if (in.flags & 0x8000u) {           /* gather/scatter: low 16 bits = uniform code of pointer */
+                in.b = rebase_code(in.b); in.c = rebase_code(in.c);
+                if (in.pad == 3) {                  /* gather/scatter: low 16 bits = uniform code of pointer */
                     uint16_t code = (uint16_t) (in.imm & 0xffffu);
                     in.imm = (in.imm & 0xffff0000u) | (rebase_code(code) & 0x7fffu);
-                    in.flags &= ~0x8000u;
-                }
-                if (in.flags & 0x4000u) {           /* stores: imm = argument-word uniform index */
+                } else if (in.pad == 1) {           /* imm = argument-word index */
                     in.imm = n_lit + (in.imm & 0x0fffu);
-                    in.flags &= ~0x4000u;
+                } else if (in.pad == 2) {           /* dst = argument-word index */
+                    in.dst = (uint16_t) (n_lit + (in.dst & 0x0fffu));
                 }
-                if (in.imm & 0x80000000u) {
-                    int op = in.op;
-                    if (op == DOP_SMEM_ZERO || op == DOP_SMEM_LOAD_TABLE || op == DOP_SMEM_FLUSH_ADD_F32 ||
-                        op == DOP_SMEM_FLUSH_ADD_I32 || op == DOP_GATHER_32_SMEM ||
-                        op == DOP_SCATTER_ADD_F32_SMEM || op == DOP_SCATTER_ADD_I32_SMEM)
-                        in.imm = n_lit + (in.imm & 0x7fffffffu);     /* descriptor index */
-                }
-                if (in.op == DOP_RFIN) in.dst = (uint16_t) (n_lit + (in.dst & 0x0fffu));
+                in.pad = 0;
             }
         };
         fix(out.init); fix(out.body); fix(out.fini);
-        /* descriptors hold the uniform code of their pointer in word 3: convert to plain index */
+        /* descriptors hold the uniform code of their pointer in word 3: convert to a plain index */
         for (EkInstr &in : out.init) {
             if (in.op == DOP_SMEM_ZERO || in.op == DOP_SMEM_LOAD_TABLE) {
                 uint32_t di = in.imm - n_lit;
@@ -855,7 +953,7 @@ struct Planner {
 };
 
 size_t smem_layout(const Assembled &a, Config &cfg, size_t n_uni) {
-    size_t off = (n_uni * 4 + 15) & ~(size_t) 15;
+    size_t off = n_uni * 16;                        /* every uniform word is replicated 4x */
     cfg.off_bar = (uint32_t) off; off += 8 * 8 + 33 * 8;
     off = (off + 15) & ~(size_t) 15;
     size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
@@ -943,11 +1041,10 @@ const char *dop_name(uint16_t op) {
     return op < DOP__COUNT ? names[op] : "?";
 }
 
-std::string opnd_str(uint16_t c, uint32_t n_tmp) {
+std::string opnd_str(uint16_t c) {
     if (c == EK_OPND_NONE) return "-";
-    if (c == EK_OPND_ACC) return "acc";
-    if (c & 0x8000u) return "u" + std::to_string(c & 0x7fffu);
-    if (c >= n_tmp) return "in" + std::to_string(c - n_tmp);
+    if (c & 0x8000u) return "u" + std::to_string(c & 0x3fffu);
+    if (c & EK_OPND_STAGED) return "in" + std::to_string(c & 0x3fffu);
     return "s" + std::to_string(c);
 }
 
@@ -956,8 +1053,7 @@ void dump_program(std::ostream &os, const Assembled &a, const Group &g) {
        << " out=" << a.outputs.size() << " ops=" << a.n_arith << " tmp_slots=" << a.n_tmp << " lits=" << a.lits.size() << "\n";
     auto sec = [&](const char *name, const std::vector<EkInstr> &v) {
         for (const EkInstr &in : v) {
-            os << "  " << name << " " << dop_name(in.op) << " a=" << opnd_str(in.a, a.n_tmp) << " b=" << opnd_str(in.b, a.n_tmp)
-               << " c=" << opnd_str(in.c, a.n_tmp);
+            os << "  " << name << " " << dop_name(in.op) << " b=" << opnd_str(in.b) << " c=" << opnd_str(in.c);
             if (in.flags & EKF_ST) os << " -> s" << in.dst;
             os << " imm=0x" << std::hex << in.imm << std::dec << "\n";
         }
@@ -1100,7 +1196,15 @@ static int eval_impl(bool dry, std::string *dump) {
         if (ctx.log_level >= 3) { std::ostringstream oss; dump_program(oss, a, g); fputs(oss.str().c_str(), stderr); }
 
         if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
-        ek_cuda_check(ek_launch_sweep(cfg.V, args, grid, cfg.T, cfg.smem, ctx.stream));
+        size_t n_prog_total = a.init.size() + a.body.size() + a.fini.size();
+        bool inline_prog = n_prog_total <= EK_INLINE_PROG;
+        if (inline_prog) {
+            EkInstr *dstp = args.prog_inline;
+            for (const EkInstr &in : a.init) *dstp++ = in;
+            for (const EkInstr &in : a.body) *dstp++ = in;
+            for (const EkInstr &in : a.fini) *dstp++ = in;
+        }
+        ek_cuda_check(ek_launch_sweep(cfg.V, inline_prog, args, grid, cfg.T, cfg.smem, ctx.stream));
         if (ctx.timing) {
             ek_cuda_check(cudaEventRecord(ctx.ev_stop, ctx.stream));
             ek_cuda_check(cudaEventSynchronize(ctx.ev_stop));

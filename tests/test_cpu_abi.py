@@ -46,8 +46,11 @@ def test_plan_c2_program(ek):
     plan = ek.debug_plan()
     assert "n=1048576 in=4" in plan and "out=1" in plan
     body = [l.split()[1] for l in plan.splitlines() if l.strip().startswith("body")]
-    assert body == ["FMA_F32", "MUL_F32", "NEG_F32", "EXP_F32", "FMA_F32", "SIN_F32", "ABS_F32", "SQRT_F32", "FMA_F32", "ST_32"]
-    # single-use temporaries are forwarded through the accumulator: only t and sin(...) need slots
+    # two-address accumulator code: x0 is loaded, every other operand is fetched from shared memory,
+    # the final fmadd takes the accumulator as its addend (FMAC)
+    assert body == ["LOAD_32", "FMA_F32", "MUL_F32", "NEG_F32", "EXP_F32", "FMA_F32", "SIN_F32", "LOAD_32", "ABS_F32",
+                    "SQRT_F32", "FMAC_F32", "ST_32"]
+    # single-use temporaries stay in the accumulator: only t and sin(...) need slots
     assert "tmp_slots=2" in plan
     del out
 
