@@ -63,6 +63,7 @@ struct Assembled {
     uint32_t n_tmp = 0, n_in_units = 0, n_red = 0;
     uint32_t extra_bytes = 0;
     uint32_t n_arith = 0;
+    bool has64 = false;                         /* any 64-bit value: needs the general (high-plane) kernel */
     uint64_t bytes_in = 0, bytes_out = 0;
     struct DescFix { uint32_t argw; uint32_t count_limit; };
     std::vector<uint32_t> copies_fix;           /* argw index of Desc.copies (set from config) */
@@ -347,6 +348,11 @@ struct Assembler {
                 if (count >= EK_MAX_STAGED || units + u > EK_STAGE_UNIT_BUDGET) direct.insert(idx);
                 else { units += u; ++count; }
             }
+        }
+
+        for (uint32_t idx : g.sched) {
+            const EkVariable &v = var(idx);
+            if (!v.direct_pointer && ek_is_64(v.type)) out.has64 = true;
         }
 
         /* ---- pass 1: emit indices, last uses, accumulator compatibility ---- */
@@ -975,8 +981,11 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
     size_t per_sm = 228 * 1024 - 1024;              /* per SM, minus the 1 KB per-CTA reservation */
     struct Cand { int V; uint32_t T; uint32_t stages; uint32_t want_ctas; };
     static const Cand cands[] = {
+        { 16, 128, 2, 2 }, { 16, 256, 2, 1 }, { 16, 128, 2, 1 },          /* 32-bit-only programs */
         { 8, 256, 2, 2 }, { 8, 256, 3, 1 }, { 8, 256, 2, 1 }, { 8, 128, 2, 2 }, { 8, 128, 2, 1 },
         { 4, 128, 2, 1 }, { 4, 64, 2, 1 }, { 4, 32, 2, 1 } };
+    size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
+    bool fast_ok = !a.has64 && n_prog <= EK_INLINE_PROG;
     if (n <= 4096) {
         /* tiny sweeps (incl. the size-1 scalar groups): one small CTA */
         static const Cand small[] = { { 4, 32, 2, 1 }, { 4, 128, 2, 1 }, { 8, 256, 2, 1 } };
@@ -987,6 +996,7 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
         }
     }
     for (const Cand &c : cands) {
+        if (c.V == 16 && !fast_ok) continue;
         cfg.V = c.V; cfg.T = c.T; cfg.stages = a.n_in_units ? c.stages : 2; cfg.ctas_per_sm = c.want_ctas;
         size_t need = smem_layout(a, cfg, n_uni);
         if (need > budget) continue;
@@ -1148,6 +1158,22 @@ static int eval_impl(bool dry, std::string *dump) {
             if (v.data == nullptr) { v.data = ek_malloc(o.bytes); v.free_data = true; v.subtree_size = 1; }
         }
 
+        /* operand codes -> (byte offset >> 4) for this configuration's shared-memory layout */
+        {
+            const uint32_t slot_bytes = cfg.T * cfg.V * 4u;
+            auto patch = [&](uint16_t code) -> uint16_t {
+                if (code == EK_OPND_NONE || (code & EK_OPND_UNI)) return code;      /* uniform index == offset >> 4 */
+                if (code & EK_OPND_STAGED) return (uint16_t) (EK_OPND_STAGED | (((code & 0x3fffu) * slot_bytes) >> 4));
+                return (uint16_t) ((cfg.off_slots + (uint32_t) code * slot_bytes) >> 4);
+            };
+            auto patch_all = [&](std::vector<EkInstr> &v) {
+                for (EkInstr &in : v) {
+                    in.b = patch(in.b); in.c = patch(in.c);
+                    if ((in.flags & EKF_ST) || in.op == DOP_RACC) in.dst = patch(in.dst);
+                }
+            };
+            patch_all(a.init); patch_all(a.body); patch_all(a.fini);
+        }
         EkSweepArgs args;
         memset(&args, 0, sizeof(args));
         lookup_program(ctx, a, args.prog, args.lit);
