@@ -297,22 +297,42 @@ struct Assembler {
 
     EkInstr mk(int op, uint32_t imm = 0) {
         EkInstr in;
-        in.op = (uint16_t) op; in.flags = 0; in.dst = 0; in.b = EK_OPND_NONE; in.c = EK_OPND_NONE; in.pad = 0; in.imm = imm;
+        in.op = (uint16_t) op; in.flags = 0; in.dst = 0; in.b = EK_OPND_NONE; in.c = EK_OPND_NONE; in.a = EK_OPND_NONE; in.imm = imm;
         return in;
     }
+    static void set_mark(EkInstr &in, uint32_t m) { in.flags = (uint16_t) ((in.flags & ~0x3000u) | (m << 12)); }
     void set_b(EkInstr &in, uint32_t v) { in.b = operand(v); in.flags |= EKF_HAS_B; if (ek_is_64(var(v).type)) in.flags |= EKF_B64; }
     void set_c(EkInstr &in, uint32_t v) { in.c = operand(v); in.flags |= EKF_HAS_C; if (ek_is_64(var(v).type)) in.flags |= EKF_C64; }
     void set_b_code(EkInstr &in, uint16_t code, bool is64) { in.b = code; in.flags |= EKF_HAS_B; if (is64) in.flags |= EKF_B64; }
     void set_c_code(EkInstr &in, uint16_t code, bool is64) { in.c = code; in.flags |= EKF_HAS_C; if (is64) in.flags |= EKF_C64; }
 
-    /* make `v` the accumulator content (emits a LOAD when it is not already there) */
+    /* make `v` the accumulator content: the load is fused into the next instruction (EKF_HAS_A) */
+    uint32_t last_emitted_for = 0; /* variable whose value the last body instruction produced */
+    uint32_t pending_a = 0;       /* variable to load into the accumulator by the next instruction */
+    uint32_t pending_mod = 0;     /* EKF_NEG_A / EKF_ABS_A to apply to the accumulator input     */
+    uint16_t pending_a_code = 0; bool pending_a_64 = false;
     void ensure_acc(uint32_t v) {
         if (acc_var == v) return;
-        bool is64 = ek_is_64(var(v).type);
-        EkInstr in = mk(is64 ? DOP_LOAD_64 : DOP_LOAD_32);
-        set_b(in, v);
-        out.body.push_back(in);
+        flush_pending();          /* (cannot stack two loads) */
+        pending_a = v;
+        pending_a_code = operand(v);      /* resolved now: the slot may be released before the push */
+        pending_a_64 = ek_is_64(var(v).type);
         acc_var = v;
+    }
+    /* append an instruction to the body, attaching the pending accumulator load / modifiers */
+    void push_body(EkInstr in) {
+        if (pending_a) {
+            in.a = pending_a_code;
+            in.flags |= EKF_HAS_A;
+            if (pending_a_64) in.flags |= EKF_A64;
+            pending_a = 0;
+        }
+        in.flags |= (uint16_t) pending_mod;
+        pending_mod = 0;
+        out.body.push_back(in);
+    }
+    void flush_pending() {
+        if (pending_a || pending_mod) push_body(mk(DOP_NOP));
     }
 
     /* give the value of `v` (just produced into the accumulator by `in`) a home */
@@ -474,9 +494,10 @@ struct Assembler {
                 }
                 uint32_t pa = arg_ptr(idx, false);
                 EkInstr in = mk(op, uni_arg(pa) & 0x7fffu);
-                in.pad = 1;                    /* marker: imm holds an argument-word index to rebase */
+                set_mark(in, 1);               /* marker: imm holds an argument-word index to rebase */
+                flush_pending();
                 place_result(in, idx);
-                out.body.push_back(in);
+                push_body(in);
                 acc_var = idx;
                 continue;
             }
@@ -485,6 +506,7 @@ struct Assembler {
             cur_e = emits[i];
             if (!emit_var(idx, (uint32_t) i)) return false;
         }
+        flush_pending();
         return finish();
     }
 
@@ -524,12 +546,12 @@ struct Assembler {
             ensure_acc(d0);
             EkInstr in = mk(DOP_RACC, (uint32_t) kind | ((uint32_t) cls << 8));
             in.dst = (uint16_t) acc;
-            out.body.push_back(in);
+            push_body(in);
             uint32_t pa = arg_ptr(idx, true);
             out.outputs.push_back({ idx, pa, 8 });
             EkInstr fi = mk(DOP_RFIN, (uint32_t) kind | ((uint32_t) cls << 8) | (ridx << 16));
             set_b_code(fi, (uint16_t) acc, w64);
-            fi.dst = (uint16_t) pa; fi.pad = 2;          /* marker: dst holds an argument-word index to rebase */
+            fi.dst = (uint16_t) pa; set_mark(fi, 2);     /* marker: dst holds an argument-word index to rebase */
             out.fini.push_back(fi);
             after();
             return out.error.empty();
@@ -602,12 +624,12 @@ struct Assembler {
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(1); out.argw.push_back(pa);
                     out.extra_bytes += (count * 4 + 15) & ~15u;
-                    EkInstr li = mk(DOP_SMEM_LOAD_TABLE, di); li.pad = 1;
+                    EkInstr li = mk(DOP_SMEM_LOAD_TABLE, di); set_mark(li, 1);
                     out.init.push_back(li);
-                    in = mk(DOP_GATHER_32_SMEM, di); in.pad = 1;
+                    in = mk(DOP_GATHER_32_SMEM, di); set_mark(in, 1);
                 } else {
                     in = mk(dop, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
-                    in.pad = 3;              /* marker: imm low 16 bits hold a uniform code to rebase */
+                    set_mark(in, 3);         /* marker: imm low 16 bits hold a uniform code to rebase */
                 }
                 put_b(in, d2);
                 if (ek_is_64(it)) in.flags |= EKF_A64;
@@ -644,13 +666,13 @@ struct Assembler {
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(copies); out.argw.push_back(pa);
                     out.extra_bytes += (count * copies * 4 + 15) & ~15u;
-                    EkInstr zi = mk(DOP_SMEM_ZERO, di); zi.pad = 1; out.init.push_back(zi);
-                    EkInstr fl = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SMEM_FLUSH_ADD_F32 : DOP_SMEM_FLUSH_ADD_I32, di); fl.pad = 1;
+                    EkInstr zi = mk(DOP_SMEM_ZERO, di); set_mark(zi, 1); out.init.push_back(zi);
+                    EkInstr fl = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SMEM_FLUSH_ADD_F32 : DOP_SMEM_FLUSH_ADD_I32, di); set_mark(fl, 1);
                     out.fini.push_back(fl);
-                    in = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SCATTER_ADD_F32_SMEM : DOP_SCATTER_ADD_I32_SMEM, di); in.pad = 1;
+                    in = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SCATTER_ADD_F32_SMEM : DOP_SCATTER_ADD_I32_SMEM, di); set_mark(in, 1);
                 } else {
                     in = mk(dop, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
-                    in.pad = 3;
+                    set_mark(in, 3);
                 }
                 put_b(in, d3);
                 put_c(in, d2);
@@ -743,20 +765,30 @@ struct Assembler {
                             op == EK_OP_FMA || op == EK_OP_NOT || op == EK_OP_CVT || op == EK_OP_FLOOR2INT || op == EK_OP_CEIL2INT;
         if (arith_narrow) nop = norm_op(t);
 
+        bool fused_mod = false;
         if (nop >= 0 && produces) {
-            out.body.push_back(in);
+            push_body(in);
             EkInstr nn = mk(nop);
             after();
             place_result(nn, idx);
-            out.body.push_back(nn);
+            push_body(nn);
             acc_var = idx;
         } else {
             after();
             if (produces) place_result(in, idx);
-            /* a pure rename (NOP) that needs no slot emits nothing at all */
-            if (!(in.op == DOP_NOP && !(in.flags & EKF_ST))) out.body.push_back(in);
+            bool will_store = produces && ((!v.side_effect && v.ref_ext > 0 && v.size == g.size) || forced.count(idx));
+            if ((in.op == DOP_NEG_F32 || in.op == DOP_ABS_F32) && !(in.flags & EKF_ST) && !will_store && !pending_mod &&
+                single_acc_consumer(idx)) {
+                /* fold -x / |x| into the consumer as an accumulator input modifier */
+                pending_mod = in.op == DOP_NEG_F32 ? EKF_NEG_A : EKF_ABS_A;
+                fused_mod = true;
+            } else if (!(in.op == DOP_NOP && !(in.flags & EKF_ST) && !pending_a && !pending_mod)) {
+                /* (a pure rename that needs no slot and carries no pending load emits nothing) */
+                push_body(in);
+            }
             if (produces) acc_var = idx;
         }
+        last_emitted_for = (!fused_mod && produces && !out.body.empty()) ? idx : 0;
 
         /* ---- output store (jit.cu:1165-1205) ---- */
         if (produces) {
@@ -766,9 +798,16 @@ struct Assembler {
                 uint32_t pa = arg_ptr(idx, true);
                 out.outputs.push_back({ idx, pa, std::max<size_t>(v.size * es, 8) });
                 int sop = es == 1 ? DOP_ST_8 : es == 2 ? DOP_ST_16 : es == 4 ? DOP_ST_32 : DOP_ST_64;
-                EkInstr st = mk(sop, pa);
-                st.pad = 1;
-                out.body.push_back(st);
+                flush_pending();
+                EkInstr *last = out.body.empty() ? nullptr : &out.body.back();
+                if (es == 4 && last && imm_free(last->op) && !(last->flags & (EKF_STG | 0x3000u)) && last_emitted_for == idx) {
+                    last->flags |= EKF_STG;            /* fused into the producing instruction */
+                    last->imm = pa; set_mark(*last, 1);
+                } else {
+                    EkInstr st = mk(sop, pa);
+                    set_mark(st, 1);
+                    push_body(st);
+                }
                 out.bytes_out += (uint64_t) v.size * es;
             }
         }
@@ -785,13 +824,36 @@ struct Assembler {
             uint32_t s = alloc_slots(is64 ? 2 : 1);
             EkInstr sp = mk(DOP_NOP);
             sp.flags |= EKF_ST | (is64 ? EKF_R64 : 0); sp.dst = (uint16_t) s;
-            out.body.push_back(sp);
+            push_body(sp);
             loc[vv] = { Loc::SLOT, (uint16_t) s };
             scratch.push_back({ s, is64 ? 2u : 1u });
         }
         if (as_b) set_b(ins, vv); else set_c(ins, vv);
     }
     std::vector<std::pair<uint32_t, uint32_t>> scratch;
+
+    /* does the instruction leave its imm field unused (so that EKF_STG can use it)? */
+    static bool imm_free(int op) {
+        if (op >= DOP_CVT_F32_I32 && op <= DOP_CVT_64_32) return false;
+        if (op >= DOP_LD_U8) return false;          /* loads, stores, gathers, scatters, reductions, smem helpers */
+        return true;
+    }
+    /* v is consumed exactly once, by the next emitted instruction, through the accumulator */
+    bool single_acc_consumer(uint32_t vidx) {
+        auto le = last_epos.find(vidx);
+        if (le == last_epos.end() || le->second != cur_e + 1 || force_slot.count(vidx)) return false;
+        /* find the consumer and make sure v appears once among its operands */
+        for (size_t i = 0; i < g.sched.size(); ++i) {
+            auto ep = epos.find(g.sched[i]);
+            if (ep == epos.end() || ep->second != cur_e + 1) continue;
+            const EkVariable &c = var(g.sched[i]);
+            if (c.data != nullptr || c.op == EK_OP_LITERAL) continue;
+            int cnt = 0;
+            for (int k = 0; k < 4; ++k) if (c.dep[k] == vidx) ++cnt;
+            return cnt == 1;
+        }
+        return false;
+    }
 
     static int reversed_op(int dop) {
         switch (dop) {
@@ -831,15 +893,17 @@ struct Assembler {
         auto fix = [&](std::vector<EkInstr> &v) {
             for (EkInstr &in : v) {
                 in.b = rebase_code(in.b); in.c = rebase_code(in.c);
-                if (in.pad == 3) {                  /* gather/scatter: low 16 bits = uniform code of pointer */
+                in.a = rebase_code(in.a);
+                uint32_t mark = (in.flags >> 12) & 3u;
+                in.flags &= ~0x3000u;
+                if (mark == 3) {                    /* gather/scatter: low 16 bits = uniform code of pointer */
                     uint16_t code = (uint16_t) (in.imm & 0xffffu);
                     in.imm = (in.imm & 0xffff0000u) | (rebase_code(code) & 0x7fffu);
-                } else if (in.pad == 1) {           /* imm = argument-word index */
+                } else if (mark == 1) {             /* imm = argument-word index */
                     in.imm = n_lit + (in.imm & 0x0fffu);
-                } else if (in.pad == 2) {           /* dst = argument-word index */
+                } else if (mark == 2) {             /* dst = argument-word index */
                     in.dst = (uint16_t) (n_lit + (in.dst & 0x0fffu));
                 }
-                in.pad = 0;
             }
         };
         fix(out.init); fix(out.body); fix(out.fini);
@@ -981,11 +1045,24 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
     size_t per_sm = 228 * 1024 - 1024;              /* per SM, minus the 1 KB per-CTA reservation */
     struct Cand { int V; uint32_t T; uint32_t stages; uint32_t want_ctas; };
     static const Cand cands[] = {
-        { 16, 128, 2, 2 }, { 16, 256, 2, 1 }, { 16, 128, 2, 1 },          /* 32-bit-only programs */
-        { 8, 256, 2, 2 }, { 8, 256, 3, 1 }, { 8, 256, 2, 1 }, { 8, 128, 2, 2 }, { 8, 128, 2, 1 },
+        /* measured on B200 (tools/cfgsweep.sh): single-buffered staging with more resident CTAs beats
+           double buffering -- the other CTAs of the SM hide the TMA latency and 16 warps hide the
+           interpreter's dependent-issue latency */
+        { 16, 256, 1, 2 }, { 16, 128, 1, 4 }, { 16, 128, 1, 3 }, { 16, 128, 2, 2 }, { 16, 128, 1, 2 },
+        { 16, 256, 2, 1 }, { 16, 128, 1, 1 },                               /* 32-bit-only programs */
+        { 8, 256, 1, 4 }, { 8, 256, 1, 3 }, { 8, 256, 2, 2 }, { 8, 256, 1, 2 }, { 8, 256, 2, 1 }, { 8, 256, 1, 1 },
+        { 8, 128, 1, 2 }, { 8, 128, 2, 1 }, { 8, 128, 1, 1 },
         { 4, 128, 2, 1 }, { 4, 64, 2, 1 }, { 4, 32, 2, 1 } };
     size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
     bool fast_ok = !a.has64 && n_prog <= EK_INLINE_PROG;
+    /* tuning aid: EK_CFG="V,T,stages,ctas_per_sm" forces a configuration for wide sweeps */
+    if (const char *env = getenv("EK_CFG")) {
+        int V, T, S, C;
+        if (n > 4096 && sscanf(env, "%d,%d,%d,%d", &V, &T, &S, &C) == 4 && (V != 16 || fast_ok)) {
+            cfg.V = V; cfg.T = (uint32_t) T; cfg.stages = (uint32_t) S; cfg.ctas_per_sm = (uint32_t) C;
+            if (smem_layout(a, cfg, n_uni) <= budget) return true;
+        }
+    }
     if (n <= 4096) {
         /* tiny sweeps (incl. the size-1 scalar groups): one small CTA */
         static const Cand small[] = { { 4, 32, 2, 1 }, { 4, 128, 2, 1 }, { 8, 256, 2, 1 } };
@@ -1063,7 +1140,12 @@ void dump_program(std::ostream &os, const Assembled &a, const Group &g) {
        << " out=" << a.outputs.size() << " ops=" << a.n_arith << " tmp_slots=" << a.n_tmp << " lits=" << a.lits.size() << "\n";
     auto sec = [&](const char *name, const std::vector<EkInstr> &v) {
         for (const EkInstr &in : v) {
-            os << "  " << name << " " << dop_name(in.op) << " b=" << opnd_str(in.b) << " c=" << opnd_str(in.c);
+            os << "  " << name << " " << dop_name(in.op);
+            if (in.flags & EKF_HAS_A) os << " a=" << opnd_str(in.a);
+            if (in.flags & EKF_NEG_A) os << " neg";
+            if (in.flags & EKF_ABS_A) os << " abs";
+            os << " b=" << opnd_str(in.b) << " c=" << opnd_str(in.c);
+            if (in.flags & EKF_STG) os << " stg";
             if (in.flags & EKF_ST) os << " -> s" << in.dst;
             os << " imm=0x" << std::hex << in.imm << std::dec << "\n";
         }
@@ -1168,7 +1250,7 @@ static int eval_impl(bool dry, std::string *dump) {
             };
             auto patch_all = [&](std::vector<EkInstr> &v) {
                 for (EkInstr &in : v) {
-                    in.b = patch(in.b); in.c = patch(in.c);
+                    in.b = patch(in.b); in.c = patch(in.c); in.a = patch(in.a);
                     if ((in.flags & EKF_ST) || in.op == DOP_RACC) in.dst = patch(in.dst);
                 }
             };

@@ -21,7 +21,7 @@ struct EkInstr {
     uint16_t flags;
     uint16_t dst;     /* slot index for the result (if EKF_ST) / accumulator slot / uniform index */
     uint16_t b, c;    /* operand codes */
-    uint16_t pad;
+    uint16_t a;       /* operand loaded into the accumulator first (EKF_HAS_A) */
     uint32_t imm;
 };
 
@@ -38,7 +38,12 @@ struct EkInstr {
 #define EKF_HAS_C 0x0008u
 #define EKF_B64   0x0010u
 #define EKF_C64   0x0020u
-#define EKF_A64   0x0040u   /* gather/scatter: the index in the accumulator is 64 bit          */
+#define EKF_A64   0x0040u   /* the accumulator value is 64 bit (gather/scatter index, HAS_A)    */
+#define EKF_HAS_A 0x0080u   /* load the accumulator from operand `a` before executing        */
+#define EKF_NEG_A 0x0100u   /* f32 input modifier: accumulator = -accumulator                 */
+#define EKF_ABS_A 0x0200u   /* f32 input modifier: accumulator = |accumulator|                */
+#define EKF_STG   0x0400u   /* after executing, store the 32-bit accumulator to the global array
+                               whose pointer is the uniform pair at index imm                 */
 
 /* rounding modes for DOP_CVT_* (imm) */
 #define EK_RZ 0
