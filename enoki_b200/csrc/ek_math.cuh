@@ -27,6 +27,11 @@ __device__ __forceinline__ uint32_t ubits(float f) { return __float_as_uint(f); 
 __device__ __forceinline__ int32_t cvtt_f32_i32(float x) {
     return (x >= -2147483648.f && x < 2147483648.f) ? __float2int_rz(x) : (int32_t) 0x80000000;
 }
+/* Saturating conversion (cvt.rzi.s32.f32) where the difference to cvttps2dq cannot be observed:
+   - sincos: the argument is >= 0; positive overflow saturates to 0x7fffffff and (j + 1) & ~1 maps it to the
+     same 0x80000000 the CPU path produces; NaN ends in NaN either way;
+   - exp: the argument is an integer in [-128, 128] unless the overflow/underflow masks or a NaN override it. */
+__device__ __forceinline__ int32_t cvtt_sat(float x) { return __float2int_rz(x); }
 
 /* array_math.h:25-33 */
 __device__ __forceinline__ float poly2(float x, float c0, float c1, float c2) {
@@ -50,7 +55,7 @@ __device__ __forceinline__ float poly8(float x, float c0, float c1, float c2, fl
 template <bool Sin, bool Cos>
 __device__ __forceinline__ void sincos(float x, float &s_out, float &c_out) {
     float xa = fabsf(x);
-    int32_t j = cvtt_f32_i32(fmul(xa, 1.2732395447351626862f));
+    int32_t j = cvtt_sat(fmul(xa, 1.2732395447351626862f));
     j = (j + 1) & ~1;
     float y = __int2float_rn(j);
     uint32_t sign_sin = ((uint32_t) j << 29) ^ ubits(x);
@@ -80,7 +85,7 @@ __device__ __forceinline__ float exp_f32(float x) {
     float z = poly5(xr, 5.0000001201e-1f, 1.6666665459e-1f, 4.1665795894e-2f,
                         8.3334519073e-3f, 1.3981999507e-3f, 1.9875691500e-4f);
     z = ffma(z, fmul(xr, xr), fadd(xr, 1.f));
-    uint32_t scale = (uint32_t) (cvtt_f32_i32(n) + 0x7f) << 23;
+    uint32_t scale = (uint32_t) (cvtt_sat(n) + 0x7f) << 23;
     float r = fmul(z, fbits(scale));
     return overflow ? __int_as_float(0x7f800000) : (underflow ? 0.f : r);
 }
