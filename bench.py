@@ -81,7 +81,17 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+        if not sm:
+            # the timed region was shorter than one sampling period: take one sample now (still warm)
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                                     capture_output=True, text=True, timeout=10).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                sm.append(float(f[1])); smax = float(f[2])
+            except Exception:
+                pass
+        busy = [v for v in sm if smax and v >= 0.5 * smax] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
 
@@ -179,7 +189,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--elems", type=int, default=N_ELEMS, help="elements per GPU (default: the BASELINE config, 2^26)")
@@ -250,12 +260,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # runs through warm-up, the timed region and the kernel-timing pass
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     L.ek_stats_reset()
     barrier()
     L.ek_timer_start()
@@ -266,7 +276,6 @@ def main():
     ms = L.ek_timer_stop()
     barrier()
     wall_ms = 1e3 * (time.time() - t0)
-    clocks = sampler.stop() if rank == 0 else None
     st = ek.stats()
     launches = int(st.launches)
     if dist is not None:
@@ -286,6 +295,7 @@ def main():
         del o, s
     stt = ek.stats()
     L.ek_set_timing(0)
+    clocks = sampler.stop() if rank == 0 else None
     kern_ms = stt.total_kernel_ms / max(int(stt.sweep_launches), 1)
     peaks = {}
     try:

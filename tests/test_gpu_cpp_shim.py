@@ -1,0 +1,20 @@
+"""Runs the C++ drop-in check (tests/cpp/shim_smoke.cpp): the reference's UNMODIFIED generic headers
+(array_router.h, array_math.h, autodiff.h, random.h ...) instantiated over this repo's
+enoki::CUDAArray<T> / Tape<CUDAArray<float>> and linked against libenoki_b200.so.  The binary is built
+in the dev container (it needs /root/reference/include at compile time only) by
+__graft_entry__.build() and travels to the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "shim_smoke")
+
+
+def test_cpp_header_shim(gpu):
+    if not os.path.exists(BIN):
+        pytest.skip("tests/cpp/shim_smoke not built (needs the reference headers at build time)")
+    r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
