@@ -248,9 +248,8 @@ def main():
         s = hsum(out) if reduce_scalar else None
         ek.cuda_eval()
         if world > 1 and s is not None:
-            with torch.cuda.stream(ext_stream):
-                ten = torch.as_tensor(DevScalar(L.ek_var_ptr(s.index)), device=f"cuda:{local_rank}")
-                dist.all_reduce(ten)
+            from enoki_b200.dist import allreduce_device_scalar
+            allreduce_device_scalar(L.ek_var_ptr(s.index), "f32", L.ek_stream(), torch.device("cuda", local_rank))
         return out, s
 
     def barrier():
@@ -432,6 +431,11 @@ def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
         ms = float(tt.item())
     ms_per = ms / steps
     edge_adjoints = int(st.edge_adjoints) // steps
+    # kernel-only time of the adjoint launches (per-launch CUDA events; serialises host and device)
+    L.ek_set_timing(1); L.ek_stats_reset()
+    run(False)
+    kern_ms = ek.stats().total_kernel_ms
+    L.ek_set_timing(0)
     # reachable sub-graph only: the runtime counts exactly the (edge, element) pairs it processed
     bytes_alg = 10.0 * edge_adjoints
     res = {"metric": "M edge-adjoints/s (backward)", "value": world * edge_adjoints / (ms_per * 1e-3) / 1e6,
@@ -441,7 +445,8 @@ def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
                         "frac": bytes_alg / (ms_per * 1e-3) / 1e9 / peak_gbs, "bytes_per_edge_adjoint": 10.0,
                         "weights_only_frac": 4.0 * edge_adjoints / (ms_per * 1e-3) / 1e9 / peak_gbs,
                         "note": "whole backward() incl. host scheduling and 80 per-level launches"},
-           "launches_per_backward": int(st.adjoint_launches) // steps}
+           "launches_per_backward": int(st.adjoint_launches) // steps, "adjoint_kernels_ms_sum": kern_ms,
+           "adjoint_kernels_frac": bytes_alg / (kern_ms * 1e-3) / 1e9 / peak_gbs}
     # final pass frees the graph; leaf gradients stay readable
     run(True)
     g = L.ek_tape_gradient(F32, ids[0][0])
