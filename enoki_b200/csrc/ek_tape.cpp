@@ -336,23 +336,33 @@ int backward_impl(Tape &T, bool free_graph) {
     if (ek_init() != 0) return -1;
     if (free_graph) for (uint32_t idx : sched) inc_ref_ext(T, idx);
     const size_t es = ek_type_size(T.vt);
+    const size_t S = sched.size();
 
-    /* ---- levels: longest distance from a root over out-edges ---- */
-    std::unordered_map<uint32_t, uint32_t> pos;
-    pos.reserve(sched.size() * 2);
-    for (size_t i = 0; i < sched.size(); ++i) pos[sched[i]] = (uint32_t) i;
-    std::vector<uint32_t> level(sched.size(), 0), remaining(sched.size(), 0);
+    /* ---- one pass over the reachable sub-graph: node pointers, out-edge lists (sorted by
+            descending target id because targets are visited in descending id), levels = longest
+            distance from a root over out-edges ---- */
+    struct SNode {
+        TNode *n = nullptr;
+        uint32_t level = 0, remaining = 0;
+        std::vector<std::pair<uint32_t, TEdge *>> out;      /* (target position, edge) */
+    };
+    std::vector<SNode> sn(S);
+    const uint32_t id_base = sched.front();
+    std::vector<uint32_t> pos_of(sched.back() - id_base + 1, UINT32_MAX);
+    for (size_t i = 0; i < S; ++i) { pos_of[sched[i] - id_base] = (uint32_t) i; sn[i].n = node(T, sched[i]); }
     uint32_t max_level = 0;
     bool need_eval = false;
     size_t total_terms = 0;
-    for (size_t i = sched.size(); i-- > 0;) {
-        TNode &t = *node(T, sched[i]);
-        remaining[i] = (uint32_t) t.edges.size();
-        for (const TEdge &e : t.edges) {
-            auto p = pos.find(e.source);
-            if (p == pos.end()) continue;
-            level[p->second] = std::max(level[p->second], level[i] + 1);
-            max_level = std::max(max_level, level[p->second]);
+    for (size_t i = S; i-- > 0;) {
+        TNode &t = *sn[i].n;
+        sn[i].remaining = (uint32_t) t.edges.size();
+        for (TEdge &e : t.edges) {
+            if (e.source < id_base || e.source - id_base >= pos_of.size()) continue;
+            uint32_t p = pos_of[e.source - id_base];
+            if (p == UINT32_MAX) continue;
+            sn[p].level = std::max(sn[p].level, sn[i].level + 1);
+            max_level = std::max(max_level, sn[p].level);
+            sn[p].out.emplace_back((uint32_t) i, &e);
             ++total_terms;
             if (!e.special) {
                 const EkVariable &w = ctx.vars[e.weight];
@@ -364,10 +374,10 @@ int backward_impl(Tape &T, bool free_graph) {
     if (need_eval && ek_eval() != 0) return -1;           /* materialise all edge weights at once */
 
     std::vector<std::vector<uint32_t>> by_level(max_level + 1);
-    for (size_t i = 0; i < sched.size(); ++i) by_level[level[i]].push_back((uint32_t) i);
+    for (size_t i = 0; i < S; ++i) by_level[sn[i].level].push_back((uint32_t) i);
 
     /* ---- descriptor staging: [jobs | terms | chunk_start] per level, one H2D copy each ---- */
-    size_t need = sched.size() * (sizeof(EkAdjJob) + 4) + total_terms * sizeof(EkAdjTerm) + 64 * (max_level + 2);
+    size_t need = S * (sizeof(EkAdjJob) + 4) + total_terms * sizeof(EkAdjTerm) + 64 * (max_level + 2);
     if (need > T.stage_bytes) {
         if (T.stage_done) { ek_cuda_check(cudaEventSynchronize(T.stage_done)); }
         if (T.h_stage) ek_host_free(T.h_stage);
@@ -380,69 +390,57 @@ int backward_impl(Tape &T, bool free_graph) {
     else ek_cuda_check(cudaEventSynchronize(T.stage_done));   /* previous backward() has consumed the staging area */
     size_t stage_off = 0;
 
-    auto finalize_if_done = [&](uint32_t p) {
-        if (remaining[p] == 0) finalize_target(T, sched[p], free_graph);
-    };
-
     /* roots / level 0: nothing to accumulate; leaves among them are finalised at once */
-    for (uint32_t p : by_level[0]) {
-        TNode &t = *node(T, sched[p]);
-        if (t.edges.empty()) finalize_target(T, sched[p], free_graph);
-    }
+    for (uint32_t p : by_level[0])
+        if (sn[p].n->edges.empty()) finalize_target(T, sched[p], free_graph);
 
-    std::vector<std::pair<uint32_t, TEdge *>> out;
-    std::vector<EkAdjJob> jobs;
-    std::vector<EkAdjTerm> terms;
-    std::vector<uint32_t> chunk_start;
-    std::vector<uint32_t> job_pos;
+    std::vector<uint32_t> done, generic;
+    uint8_t *hst = (uint8_t *) T.h_stage, *dst_dev = (uint8_t *) T.d_stage;
 
     for (uint32_t L = 1; L <= max_level; ++L) {
-        jobs.clear(); terms.clear(); chunk_start.clear(); job_pos.clear();
-        uint32_t n_chunks = 0;
-        std::vector<uint32_t> generic;
-        bool level_needs_eval = false;
-
-        /* pass 1: which target gradients of this level are still unevaluated traces? */
-        for (uint32_t p : by_level[L]) {
-            TNode &s = *node(T, sched[p]);
-            for (uint32_t tid : s.edges_rev) {
-                auto tp = pos.find(tid); if (tp == pos.end()) continue;
-                TNode &t = *node(T, tid);
-                if (!t.grad) continue;
-                uint64_t bits;
-                if (ctx.vars[t.grad].data == nullptr && !var_imm(t.grad, bits)) level_needs_eval = true;
-            }
-        }
-        if (level_needs_eval && ek_eval() != 0) return -1;
+        done.clear(); generic.clear();
+        /* descriptors are written straight into the pinned staging area */
+        const size_t n_src = by_level[L].size();
+        size_t n_terms_lvl = 0;
+        for (uint32_t p : by_level[L]) n_terms_lvl += sn[p].out.size();
+        size_t o_jobs = stage_off, o_terms = (o_jobs + n_src * sizeof(EkAdjJob) + 15) & ~(size_t) 15;
+        size_t o_chunks = (o_terms + n_terms_lvl * sizeof(EkAdjTerm) + 15) & ~(size_t) 15;
+        size_t end_max = (o_chunks + n_src * 4 + 15) & ~(size_t) 15;
+        if (end_max > T.stage_bytes) { ek_set_error("backward(): internal error: staging overflow"); return -1; }
+        EkAdjJob *jobs = (EkAdjJob *) (hst + o_jobs);
+        EkAdjTerm *terms = (EkAdjTerm *) (hst + o_terms);
+        uint32_t *chunk_start = (uint32_t *) (hst + o_chunks);
+        uint32_t n_jobs = 0, n_terms = 0, n_chunks = 0;
 
         for (uint32_t p : by_level[L]) {
-            uint32_t sidx = sched[p];
-            TNode &s = *node(T, sidx);
-            out.clear();
-            for (uint32_t tid : s.edges_rev) {
-                if (!pos.count(tid)) continue;
-                TNode &t = *node(T, tid);
-                for (TEdge &e : t.edges) if (e.source == sidx) out.emplace_back(tid, &e);
-            }
-            std::sort(out.begin(), out.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
-
+            SNode &S_ = sn[p];
+            TNode &s = *S_.n;
+            /* classify */
             bool simple = s.grad == 0;
-            for (auto &te : out) {
-                TNode &t = *node(T, te.first);
+            for (auto &te : S_.out) {
+                if (!simple) break;
+                TNode &t = *sn[te.first].n;
                 if (te.second->special) { simple = false; break; }
-                size_t ws = ek_var_size(te.second->weight);
-                size_t gs = t.grad ? ek_var_size(t.grad) : 1;
+                const EkVariable &w = ctx.vars[te.second->weight];
+                size_t ws = w.size, gs = t.grad ? ctx.vars[t.grad].size : 1;
                 if (s.size == 1 && (ws != 1 || gs != 1)) { simple = false; break; }
                 if ((ws != 1 && ws != s.size) || (gs != 1 && gs != s.size)) { simple = false; break; }
+                if (t.grad) {
+                    uint64_t bits;
+                    if (ctx.vars[t.grad].data == nullptr && !var_imm(t.grad, bits)) {
+                        /* adjoint produced by the generic path and still an unevaluated trace */
+                        if (ek_eval() != 0) return -1;
+                    }
+                }
             }
             if (!simple) { generic.push_back(p); continue; }
 
             EkAdjJob job;
-            job.first_term = (uint32_t) terms.size(); job.n_terms = 0; job.size = s.size; job.aligned = 1;
-            for (auto &te : out) {
-                TNode &t = *node(T, te.first);
+            job.first_term = n_terms; job.n_terms = 0; job.size = s.size; job.aligned = 1;
+            for (auto &te : S_.out) {
+                TNode &t = *sn[te.first].n;
                 if (!t.grad) continue;                      /* empty adjoint contributes nothing */
-                EkAdjTerm term; term.pad = 0;
+                EkAdjTerm &term = terms[n_terms]; term.pad = 0;
                 uint32_t wk, gk; uint64_t bits;
                 const EkVariable &w = ctx.vars[te.second->weight];
                 if (w.data != nullptr) { wk = w.size == 1 ? EK_ADJ_SCALAR : EK_ADJ_ARRAY; term.w = (uint64_t) (uintptr_t) w.data; }
@@ -454,35 +452,27 @@ int backward_impl(Tape &T, bool free_graph) {
                 else { ek_set_error("backward(): internal error: target adjoint not materialised"); return -1; }
                 if ((wk == EK_ADJ_ARRAY && (term.w & 15u)) || (gk == EK_ADJ_ARRAY && (term.g & 15u))) job.aligned = 0;
                 term.flags = wk | (gk << 2);
-                terms.push_back(term);
-                job.n_terms++;
-                ctx.stats.edge_adjoints += s.size;
+                ++n_terms; job.n_terms++;
             }
+            ctx.stats.edge_adjoints += (uint64_t) job.n_terms * s.size;
             if (job.n_terms > 0) {
                 void *dst = ek_malloc((size_t) s.size * es);
                 job.dst = (uint64_t) (uintptr_t) dst;
                 set_grad(s, ek_var_register(T.vt, s.size, dst, 1));
-                chunk_start.push_back(n_chunks);
+                chunk_start[n_jobs] = n_chunks;
                 n_chunks += (s.size + EK_ADJ_CHUNK - 1) / EK_ADJ_CHUNK;
-                jobs.push_back(job);
-            } else {
-                terms.resize(job.first_term);
+                jobs[n_jobs++] = job;
             }
-            job_pos.push_back(p);
+            done.push_back(p);
         }
 
-        if (!jobs.empty()) {
-            size_t jb = jobs.size() * sizeof(EkAdjJob), tb = terms.size() * sizeof(EkAdjTerm), cb = chunk_start.size() * 4;
-            size_t o_jobs = stage_off, o_terms = (o_jobs + jb + 15) & ~(size_t) 15, o_chunks = (o_terms + tb + 15) & ~(size_t) 15;
-            size_t end = (o_chunks + cb + 15) & ~(size_t) 15;
-            if (end > T.stage_bytes) { ek_set_error("backward(): internal error: staging overflow"); return -1; }
-            uint8_t *h = (uint8_t *) T.h_stage, *d = (uint8_t *) T.d_stage;
-            memcpy(h + o_jobs, jobs.data(), jb); memcpy(h + o_terms, terms.data(), tb); memcpy(h + o_chunks, chunk_start.data(), cb);
-            ek_cuda_check(cudaMemcpyAsync(d + o_jobs, h + o_jobs, end - o_jobs, cudaMemcpyHostToDevice, ctx.stream));
+        if (n_jobs) {
+            size_t end = (o_chunks + (size_t) n_jobs * 4 + 15) & ~(size_t) 15;
+            ek_cuda_check(cudaMemcpyAsync(dst_dev + o_jobs, hst + o_jobs, end - o_jobs, cudaMemcpyHostToDevice, ctx.stream));
             unsigned grid = std::min<uint32_t>(n_chunks, (uint32_t) ctx.num_sms * 8u);
             if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
-            ek_cuda_check(ek_launch_adjoint(T.vt == EK_FLOAT64, (const EkAdjJob *) (d + o_jobs), (const EkAdjTerm *) (d + o_terms),
-                                            (const uint32_t *) (d + o_chunks), (uint32_t) jobs.size(), n_chunks, grid, ctx.stream));
+            ek_cuda_check(ek_launch_adjoint(T.vt == EK_FLOAT64, (const EkAdjJob *) (dst_dev + o_jobs), (const EkAdjTerm *) (dst_dev + o_terms),
+                                            (const uint32_t *) (dst_dev + o_chunks), n_jobs, n_chunks, grid, ctx.stream));
             if (ctx.timing) {
                 ek_cuda_check(cudaEventRecord(ctx.ev_stop, ctx.stream));
                 ek_cuda_check(cudaEventSynchronize(ctx.ev_stop));
@@ -495,45 +485,28 @@ int backward_impl(Tape &T, bool free_graph) {
 
         /* generic sources of this level (special edges, hsum into scalars, pre-seeded grads) */
         for (uint32_t p : generic) {
-            uint32_t sidx = sched[p];
-            TNode &s = *node(T, sidx);
-            out.clear();
-            for (uint32_t tid : s.edges_rev) {
-                if (!pos.count(tid)) continue;
-                TNode &t = *node(T, tid);
-                for (TEdge &e : t.edges) if (e.source == sidx) out.emplace_back(tid, &e);
-            }
-            std::sort(out.begin(), out.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
-            if (accumulate_generic(T, sidx, s, out) != 0) return -1;
-            job_pos.push_back(p);
+            std::vector<std::pair<uint32_t, TEdge *>> out;
+            out.reserve(sn[p].out.size());
+            for (auto &te : sn[p].out) out.emplace_back(sched[te.first], te.second);
+            if (accumulate_generic(T, sched[p], *sn[p].n, out) != 0) return -1;
+            done.push_back(p);
         }
 
         /* bookkeeping: every processed source has consumed one in-edge of each of its targets */
-        for (uint32_t p : job_pos) {
-            uint32_t sidx = sched[p];
-            std::vector<uint32_t> targets;
-            {
-                TNode &s = *node(T, sidx);
-                for (uint32_t tid : s.edges_rev) if (pos.count(tid)) targets.push_back(tid);
+        for (uint32_t p : done) {
+            for (auto &te : sn[p].out) {
+                SNode &tn = sn[te.first];
+                if (tn.remaining > 0 && --tn.remaining == 0) finalize_target(T, sched[te.first], free_graph);
             }
-            for (uint32_t tid : targets) {
-                uint32_t tp = pos[tid];
-                auto it = T.nodes.find(tid);
-                if (it == T.nodes.end()) continue;
-                uint32_t cnt = 0;
-                for (const TEdge &e : it->second.edges) if (e.source == sidx) ++cnt;
-                remaining[tp] -= std::min(remaining[tp], cnt);
-                finalize_if_done(tp);
-            }
+            sn[p].out.clear();
             /* a source without in-edges (leaf) is complete now */
-            auto sit = T.nodes.find(sidx);
-            if (sit != T.nodes.end() && sit->second.edges.empty()) finalize_target(T, sidx, free_graph);
+            if (sn[p].remaining == 0 && sn[p].n->edges.empty()) finalize_target(T, sched[p], free_graph);
         }
     }
     ek_cuda_check(cudaEventRecord(T.stage_done, ctx.stream));
 
     if (T.log_level >= 1)
-        fprintf(stderr, "autodiff: backward(): processed %zu/%u nodes.\n", sched.size(), T.node_counter - T.node_counter_last);
+        fprintf(stderr, "autodiff: backward(): processed %zu/%u nodes.\n", S, T.node_counter - T.node_counter_last);
     if (free_graph) T.node_counter_last = T.node_counter;
     T.scheduled.clear();
     return 0;
