@@ -344,8 +344,13 @@ int backward_impl(Tape &T, bool free_graph) {
     struct SNode {
         TNode *n = nullptr;
         uint32_t level = 0, remaining = 0;
+        int32_t block = -1;                                  /* level block that holds this node's adjoint */
         std::vector<std::pair<uint32_t, TEdge *>> out;      /* (target position, edge) */
     };
+    /* adjoints of interior nodes of one level share ONE allocation (views into it); the block goes back
+       to the allocator when the last of them has been consumed.  Leaves keep individual buffers: their
+       gradients outlive backward(). */
+    struct LevelBlock { void *base = nullptr; uint32_t pending = 0; };
     std::vector<SNode> sn(S);
     const uint32_t id_base = sched.front();
     std::vector<uint32_t> pos_of(sched.back() - id_base + 1, UINT32_MAX);
@@ -391,11 +396,23 @@ int backward_impl(Tape &T, bool free_graph) {
     size_t stage_off = 0;
 
     /* roots / level 0: nothing to accumulate; leaves among them are finalised at once */
-    for (uint32_t p : by_level[0])
-        if (sn[p].n->edges.empty()) finalize_target(T, sched[p], free_graph);
-
     std::vector<uint32_t> done, generic;
     uint8_t *hst = (uint8_t *) T.h_stage, *dst_dev = (uint8_t *) T.d_stage;
+    std::vector<LevelBlock> blocks(max_level + 1);
+    bool any_generic = false;
+    /* (a gradient that the generic path leaves as an unevaluated trace may read views of several blocks) */
+    auto finalize = [&](uint32_t p) {
+        finalize_target(T, sched[p], free_graph);
+        int32_t b = sn[p].block;
+        if (b >= 0) {
+            sn[p].block = -1;
+            if (--blocks[b].pending == 0 && !any_generic && blocks[b].base) { ek_free(blocks[b].base); blocks[b].base = nullptr; }
+        }
+    };
+
+    /* roots / level 0: nothing to accumulate; leaves among them are finalised at once */
+    for (uint32_t p : by_level[0])
+        if (sn[p].n->edges.empty()) finalize(p);
 
     for (uint32_t L = 1; L <= max_level; ++L) {
         done.clear(); generic.clear();
@@ -411,6 +428,10 @@ int backward_impl(Tape &T, bool free_graph) {
         EkAdjTerm *terms = (EkAdjTerm *) (hst + o_terms);
         uint32_t *chunk_start = (uint32_t *) (hst + o_chunks);
         uint32_t n_jobs = 0, n_terms = 0, n_chunks = 0;
+        size_t block_bytes = 0, block_off = 0;
+        for (uint32_t p : by_level[L])
+            if (!sn[p].n->edges.empty()) block_bytes += ((size_t) sn[p].n->size * es + 511) & ~(size_t) 511;
+        if (block_bytes) blocks[L].base = ek_malloc(block_bytes);
 
         for (uint32_t p : by_level[L]) {
             SNode &S_ = sn[p];
@@ -433,7 +454,7 @@ int backward_impl(Tape &T, bool free_graph) {
                     }
                 }
             }
-            if (!simple) { generic.push_back(p); continue; }
+            if (!simple) { generic.push_back(p); any_generic = true; continue; }
 
             EkAdjJob job;
             job.first_term = n_terms; job.n_terms = 0; job.size = s.size; job.aligned = 1;
@@ -456,9 +477,17 @@ int backward_impl(Tape &T, bool free_graph) {
             }
             ctx.stats.edge_adjoints += (uint64_t) job.n_terms * s.size;
             if (job.n_terms > 0) {
-                void *dst = ek_malloc((size_t) s.size * es);
+                void *dst;
+                if (!s.edges.empty()) {                        /* interior node: view into the level block */
+                    dst = (uint8_t *) blocks[L].base + block_off;
+                    block_off += ((size_t) s.size * es + 511) & ~(size_t) 511;
+                    S_.block = (int32_t) L; blocks[L].pending++;
+                    set_grad(s, ek_var_register(T.vt, s.size, dst, 0));
+                } else {                                       /* leaf: its gradient outlives backward() */
+                    dst = ek_malloc((size_t) s.size * es);
+                    set_grad(s, ek_var_register(T.vt, s.size, dst, 1));
+                }
                 job.dst = (uint64_t) (uintptr_t) dst;
-                set_grad(s, ek_var_register(T.vt, s.size, dst, 1));
                 chunk_start[n_jobs] = n_chunks;
                 n_chunks += (s.size + EK_ADJ_CHUNK - 1) / EK_ADJ_CHUNK;
                 jobs[n_jobs++] = job;
@@ -496,14 +525,23 @@ int backward_impl(Tape &T, bool free_graph) {
         for (uint32_t p : done) {
             for (auto &te : sn[p].out) {
                 SNode &tn = sn[te.first];
-                if (tn.remaining > 0 && --tn.remaining == 0) finalize_target(T, sched[te.first], free_graph);
+                if (tn.remaining > 0 && --tn.remaining == 0) finalize(te.first);
             }
             sn[p].out.clear();
             /* a source without in-edges (leaf) is complete now */
-            if (sn[p].remaining == 0 && sn[p].n->edges.empty()) finalize_target(T, sched[p], free_graph);
+            if (sn[p].remaining == 0 && sn[p].n->edges.empty()) finalize(p);
         }
+        if (blocks[L].base && blocks[L].pending == 0 && !any_generic) { ek_free(blocks[L].base); blocks[L].base = nullptr; }
     }
     ek_cuda_check(cudaEventRecord(T.stage_done, ctx.stream));
+    /* blocks that could not be released early (the generic path may hold unevaluated traces that read
+       adjoint views): evaluate, then release */
+    bool left = false;
+    for (auto &b : blocks) left |= b.base != nullptr;
+    if (left) {
+        if (any_generic && ek_eval() != 0) return -1;
+        for (auto &b : blocks) if (b.base) { ek_free(b.base); b.base = nullptr; }
+    }
 
     if (T.log_level >= 1)
         fprintf(stderr, "autodiff: backward(): processed %zu/%u nodes.\n", S, T.node_counter - T.node_counter_last);
