@@ -64,6 +64,8 @@ struct Assembled {
     uint32_t extra_bytes = 0;
     uint32_t n_arith = 0;
     bool has64 = false;                         /* any 64-bit value: needs the general (high-plane) kernel */
+    uint32_t release_mask = 0;                  /* staged inputs released by the EKF_REL instruction (single-stage configs) */
+    int release_at = -1;                        /* body index of that instruction */
     uint64_t bytes_in = 0, bytes_out = 0;
     struct DescFix { uint32_t argw; uint32_t count_limit; };
     std::vector<uint32_t> copies_fix;           /* argw index of Desc.copies (set from config) */
@@ -871,6 +873,44 @@ struct Assembler {
         }
     }
 
+    /* Early release (single-buffered staging): find the body instruction after which most staged bytes are
+       dead while most of the tile's work is still ahead; the kernel starts streaming those inputs for the
+       CTA's next tile right there. */
+    void plan_release() {
+        size_t ns = out.staged.size(), nb = out.body.size();
+        if (ns == 0 || ns > 16 || nb < 3) return;
+        std::vector<int> last(ns, -1);
+        auto unit_of = [&](uint16_t code) -> int { return (code != EK_OPND_NONE && !(code & 0x8000u) && (code & EK_OPND_STAGED)) ? (int) (code & 0x3fffu) : -1; };
+        for (size_t i = 0; i < nb; ++i) {
+            const EkInstr &in = out.body[i];
+            int u[3] = { (in.flags & EKF_HAS_A) ? unit_of(in.a) : -1,
+                         ((in.flags & EKF_HAS_B) || (in.op >= DOP_LD_U8 && in.op <= DOP_LD_64)) ? unit_of(in.b) : -1,
+                         (in.flags & EKF_HAS_C) ? unit_of(in.c) : -1 };
+            for (int q = 0; q < 3; ++q) {
+                if (u[q] < 0) continue;
+                for (size_t k = 0; k < ns; ++k) if (out.staged[k].unit == u[q]) last[k] = (int) i;
+            }
+        }
+        double best = 0; int best_i = -1; uint32_t best_mask = 0;
+        size_t total_bytes = 0;
+        for (size_t k = 0; k < ns; ++k) total_bytes += out.staged[k].esize;
+        /* heavier instructions weigh more: transcendental ~ 8, others 1 */
+        auto weight = [&](const EkInstr &in) -> double {
+            switch (in.op) { case DOP_SIN_F32: case DOP_COS_F32: case DOP_EXP_F32: case DOP_LOG_F32: return 8.0;
+                             case DOP_SQRT_F32: case DOP_DIV_F32: case DOP_RCP_F32: case DOP_RSQRT_F32: return 3.0; default: return 1.0; } };
+        double total_w = 0; for (const EkInstr &in : out.body) total_w += weight(in);
+        double acc_w = 0;
+        for (size_t i = 0; i + 1 < nb; ++i) {
+            acc_w += weight(out.body[i]);
+            uint32_t mask = 0; size_t bytes = 0;
+            for (size_t k = 0; k < ns; ++k) if (last[k] <= (int) i) { mask |= 1u << k; bytes += out.staged[k].esize; }
+            if (!mask) continue;
+            double score = ((double) bytes / total_bytes) * ((total_w - acc_w) / total_w);
+            if (score > best) { best = score; best_i = (int) i; best_mask = mask; }
+        }
+        if (best_i >= 0 && best >= 0.15) { out.release_at = best_i; out.release_mask = best_mask; }
+    }
+
     /* rebase uniform indices now that the literal count is known:
        pool = [literals | argument words | scalar pairs] */
     bool finish() {
@@ -907,6 +947,7 @@ struct Assembler {
             }
         };
         fix(out.init); fix(out.body); fix(out.fini);
+        plan_release();
         /* descriptors hold the uniform code of their pointer in word 3: convert to a plain index */
         for (EkInstr &in : out.init) {
             if (in.op == DOP_SMEM_ZERO || in.op == DOP_SMEM_LOAD_TABLE) {
@@ -1146,6 +1187,7 @@ void dump_program(std::ostream &os, const Assembled &a, const Group &g) {
             if (in.flags & EKF_ABS_A) os << " abs";
             os << " b=" << opnd_str(in.b) << " c=" << opnd_str(in.c);
             if (in.flags & EKF_STG) os << " stg";
+            if (in.flags & EKF_REL) os << " rel";
             if (in.flags & EKF_ST) os << " -> s" << in.dst;
             os << " imm=0x" << std::hex << in.imm << std::dec << "\n";
         }
@@ -1304,6 +1346,7 @@ static int eval_impl(bool dry, std::string *dump) {
         if (ctx.log_level >= 3) { std::ostringstream oss; dump_program(oss, a, g); fputs(oss.str().c_str(), stderr); }
 
         if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
+        if (cfg.stages == 1 && a.release_at >= 0) { a.body[a.release_at].flags |= EKF_REL; args.release_mask = a.release_mask; }
         size_t n_prog_total = a.init.size() + a.body.size() + a.fini.size();
         bool inline_prog = n_prog_total <= EK_INLINE_PROG;
         if (inline_prog) {

@@ -42,6 +42,8 @@ struct EkInstr {
 #define EKF_HAS_A 0x0080u   /* load the accumulator from operand `a` before executing        */
 #define EKF_NEG_A 0x0100u   /* f32 input modifier: accumulator = -accumulator                 */
 #define EKF_ABS_A 0x0200u   /* f32 input modifier: accumulator = |accumulator|                */
+#define EKF_REL   0x0800u   /* after executing: the staged inputs in args.release_mask are dead for this tile --
+                               start streaming them for the CTA's next tile (single-buffered pipelines)   */
 #define EKF_STG   0x0400u   /* after executing, store the 32-bit accumulator to the global array
                                whose pointer is the uniform pair at index imm                 */
 
@@ -160,6 +162,7 @@ struct EkSweepArgs {
     uint32_t smem_prog_off;        /*   mbarriers+reduction scratch, program copy,            */
     uint32_t smem_extra_off;       /*   privatised bins / staged tables,                      */
     uint32_t smem_slots_off;       /*   slot file (1024-byte aligned)                         */
+    uint32_t release_mask;         /* staged inputs (bit k) released early by the EKF_REL instruction */
     uint32_t prog_in_smem;         /* (global-memory programs) copy the program to shared memory */
     uint32_t n_red;                /* number of reductions                                    */
     uint64_t *red_partials;        /* [n_red][grid] 8-byte partials                           */
