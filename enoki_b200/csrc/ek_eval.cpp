@@ -1346,7 +1346,10 @@ static int eval_impl(bool dry, std::string *dump) {
         if (ctx.log_level >= 3) { std::ostringstream oss; dump_program(oss, a, g); fputs(oss.str().c_str(), stderr); }
 
         if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
-        if (cfg.stages == 1 && a.release_at >= 0) { a.body[a.release_at].flags |= EKF_REL; args.release_mask = a.release_mask; }
+        /* measured on B200: the mid-tile CTA barrier the early release needs costs more than the hidden TMA
+           latency gains (0.467 ms vs 0.400 ms on C2) -- kept behind EK_REL=1 for experiments */
+        static const bool use_rel = getenv("EK_REL") != nullptr;
+        if (use_rel && cfg.stages == 1 && a.release_at >= 0) { a.body[a.release_at].flags |= EKF_REL; args.release_mask = a.release_mask; }
         size_t n_prog_total = a.init.size() + a.body.size() + a.fini.size();
         bool inline_prog = n_prog_total <= EK_INLINE_PROG;
         if (inline_prog) {

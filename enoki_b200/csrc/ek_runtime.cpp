@@ -93,7 +93,7 @@ int ek_init(void) {
     ek_cuda_check(cudaEventCreate(&ctx.ev_stop));
     ek_cuda_check(cudaEventCreate(&ctx.tm_start));
     ek_cuda_check(cudaEventCreate(&ctx.tm_stop));
-    ctx.max_grid = (uint32_t) ctx.num_sms * 8u;
+    ctx.max_grid = (uint32_t) ctx.num_sms * 32u;
     ek_cuda_check(cudaMalloc(&ctx.red_partials, sizeof(uint64_t) * EK_MAX_RED * ctx.max_grid));
     ek_cuda_check(cudaMalloc(&ctx.red_counters, sizeof(uint32_t) * EK_MAX_RED));
     ek_cuda_check(cudaMemset(ctx.red_counters, 0, sizeof(uint32_t) * EK_MAX_RED));
