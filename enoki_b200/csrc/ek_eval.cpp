@@ -64,6 +64,7 @@ struct Assembled {
     uint32_t extra_bytes = 0;
     uint32_t n_arith = 0;
     bool has64 = false;                         /* any 64-bit value: needs the general (high-plane) kernel */
+    bool noncore = false;                       /* uses an op that is compiled out of the V=16 fast kernel */
     uint32_t release_mask = 0;                  /* staged inputs released by the EKF_REL instruction (single-stage configs) */
     int release_at = -1;                        /* body index of that instruction */
     uint64_t bytes_in = 0, bytes_out = 0;
@@ -948,6 +949,19 @@ struct Assembler {
         };
         fix(out.init); fix(out.body); fix(out.fini);
         plan_release();
+        for (const EkInstr &in : out.body) {
+            switch (in.op) {
+                case DOP_DIV_I32: case DOP_DIVR_I32: case DOP_DIV_U32: case DOP_DIVR_U32: case DOP_MOD_I32: case DOP_MODR_I32:
+                case DOP_MOD_U32: case DOP_MODR_U32: case DOP_MULHI_I32: case DOP_MULHI_U32: case DOP_POPC_32: case DOP_CLZ_32:
+                case DOP_CTZ_32: case DOP_SEXT8: case DOP_SEXT16: case DOP_ZEXT8: case DOP_ZEXT16: case DOP_SHLR_32:
+                case DOP_SHRR_I32: case DOP_SHRR_U32: case DOP_MINR_F32: case DOP_MAXR_F32: case DOP_DIVR_F32:
+                case DOP_LD_U16: case DOP_LD_S16: case DOP_LDG_U8: case DOP_LDG_S8: case DOP_LDG_U16: case DOP_LDG_S16:
+                case DOP_ST_16: case DOP_GATHER_U8: case DOP_GATHER_S8: case DOP_GATHER_U16: case DOP_GATHER_S16:
+                case DOP_SCATTER_8: case DOP_SCATTER_16:
+                    out.noncore = true; break;
+                default: break;
+            }
+        }
         /* descriptors hold the uniform code of their pointer in word 3: convert to a plain index */
         for (EkInstr &in : out.init) {
             if (in.op == DOP_SMEM_ZERO || in.op == DOP_SMEM_LOAD_TABLE) {
@@ -1095,7 +1109,7 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
         { 8, 128, 1, 2 }, { 8, 128, 2, 1 }, { 8, 128, 1, 1 },
         { 4, 128, 2, 1 }, { 4, 64, 2, 1 }, { 4, 32, 2, 1 } };
     size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
-    bool fast_ok = !a.has64 && n_prog <= EK_INLINE_PROG;
+    bool fast_ok = !a.has64 && !a.noncore && n_prog <= EK_INLINE_PROG;
     /* tuning aid: EK_CFG="V,T,stages,ctas_per_sm" forces a configuration for wide sweeps */
     if (const char *env = getenv("EK_CFG")) {
         int V, T, S, C;
