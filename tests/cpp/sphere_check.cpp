@@ -1,0 +1,102 @@
+/* C5 parity check: differentiable ray-sphere render, forward + backward, the SAME template
+   instantiated over the reference CPU path (DiffArray<DynamicArray<Packet<float,8>>> + the reference's
+   own tape, oracle/_ref/autodiff_off.o) and over this backend (DiffArray<CUDAArray<float>> through
+   <enoki/cuda.h> / <enoki/autodiff_b200.h> of this repo).  Compares the image, the loss and the six
+   scalar gradients.  Scene after tests/sphere.cpp:58-88 of the reference (orthographic rays, unit
+   sphere, one directional light); written from scratch.  Usage: sphere_check [resolution] */
+#include <enoki/autodiff.h>
+#include <enoki/cuda.h>
+#include <enoki/dynamic.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <chrono>
+#include <vector>
+
+using namespace enoki;
+
+template <typename Float> struct Scene {
+    using Vec3 = Array<Float, 3>;
+    Vec3 delta;      /* ray-origin offset (differentiable) */
+    Vec3 light;      /* light direction (differentiable)   */
+};
+
+template <typename Float> Float render(const Float &px, const Float &py, const Scene<Float> &sc) {
+    using Vec3 = Array<Float, 3>;
+    Vec3 o = Vec3(px, py, Float(-1.f)) + sc.delta;
+    Vec3 d(Float(0.f), Float(0.f), Float(1.f));
+    Float a = dot(d, d), b = 2.f * dot(o, d), c = dot(o, o) - 1.f;
+    Float disc = b * b - 4.f * a * c;
+    Float t = (-b - sqrt(max(disc, 0.f))) / (2.f * a);
+    Vec3 n = o + d * t;                                  /* unit sphere: hit point == normal */
+    Float shade = 0.2f + max(dot(n, sc.light), 0.f) * 0.9f;
+    return select(disc >= 0.f, shade, Float(0.f));
+}
+
+template <typename FloatD, typename Float = std::decay_t<decltype(detach(std::declval<const FloatD &>()))>>
+void run(size_t res, const std::vector<float> &target, std::vector<float> &img_out, float &loss_out, float grads[6]) {
+    using UInt = uint32_array_t<Float>;
+    size_t n = res * res;
+    /* pixel grid without meshgrid(): index arithmetic (exercises integer div/mod on the device) */
+    UInt idx = arange<UInt>(n);
+    Float fx = Float(idx % (uint32_t) res), fy = Float(idx / (uint32_t) res);
+    Float step = 2.4f / float(res - 1);
+    FloatD px = FloatD(fmadd(fx, step, -1.2f)), py = FloatD(fmadd(fy, step, -1.2f));
+    Scene<FloatD> sc;
+    using Vec3D = Array<FloatD, 3>;
+    sc.delta = Vec3D(FloatD(0.05f), FloatD(-0.03f), FloatD(0.02f));
+    float il = 1.f / std::sqrt(6.f);
+    sc.light = Vec3D(FloatD(-il), FloatD(-il), FloatD(-2.f * il));
+    for (int k = 0; k < 3; ++k) { set_requires_gradient(sc.delta[k]); set_requires_gradient(sc.light[k]); }
+    FloatD img = render<FloatD>(px, py, sc);
+    Float imgv = detach(img);
+    img_out.resize(n);
+    if constexpr (is_cuda_array_v<Float>) { imgv.eval(); cuda_memcpy_from_device(img_out.data(), imgv.data(), n * 4); }
+    else memcpy(img_out.data(), imgv.data(), n * 4);
+    FloatD tgt;
+    if (target.empty()) tgt = FloatD(zero<Float>(n));
+    else tgt = FloatD(Float::copy(target.data(), n));
+    FloatD diff = img - tgt;
+    FloatD loss = hsum(diff * diff) / float(n);
+    loss_out = detach(loss).coeff(0);
+    backward(loss);
+    for (int k = 0; k < 3; ++k) { grads[k] = gradient(sc.delta[k]).coeff(0); grads[3 + k] = gradient(sc.light[k]).coeff(0); }
+}
+
+int main(int argc, char **argv) {
+    size_t res = argc > 1 ? (size_t) atoi(argv[1]) : 512;
+    if (ek_device_count() == 0) { fprintf(stderr, "no CUDA device\n"); return 2; }
+    using FloatX = DynamicArray<Packet<float, 8>>;
+    std::vector<float> none, img_cpu, img_gpu, target;
+    float loss_c, loss_g, gc[6], gg[6];
+    /* target image = render at a different offset (here: plain zero image keeps the test self-contained) */
+    auto t0 = std::chrono::high_resolution_clock::now();
+    run<DiffArray<FloatX>>(res, none, img_cpu, loss_c, gc);
+    auto t1 = std::chrono::high_resolution_clock::now();
+    run<DiffArray<CUDAArray<float>>>(res, none, img_gpu, loss_g, gg);
+    cuda_sync();
+    auto t2 = std::chrono::high_resolution_clock::now();
+    run<DiffArray<CUDAArray<float>>>(res, none, img_gpu, loss_g, gg);
+    cuda_sync();
+    auto t3 = std::chrono::high_resolution_clock::now();
+
+    size_t n = res * res, bad = 0; double maxd = 0;
+    for (size_t i = 0; i < n; ++i) {
+        double d = std::fabs((double) img_cpu[i] - img_gpu[i]);
+        maxd = std::max(maxd, d);
+        if (d > 2e-6 * std::max(1.0, std::fabs((double) img_cpu[i]))) ++bad;
+    }
+    int fail = bad != 0;
+    printf("sphere_check: %zux%zu rays  image max|diff| = %.3g (%zu px > 2e-6)\n", res, res, maxd, bad);
+    printf("  loss cpu %.8g  gpu %.8g\n", loss_c, loss_g);
+    if (std::fabs(loss_c - loss_g) > 1e-5 * std::fabs(loss_c)) fail = 1;
+    for (int k = 0; k < 6; ++k) {
+        printf("  grad[%d] cpu % .8g  gpu % .8g\n", k, gc[k], gg[k]);
+        if (std::fabs(gc[k] - gg[k]) > 2e-4 * std::max(1e-3f, std::fabs(gc[k]))) fail = 1;
+    }
+    printf("  time: cpu %.1f ms, gpu first %.1f ms, gpu second %.1f ms\n",
+           std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
+           std::chrono::duration<double, std::milli>(t3 - t2).count());
+    printf(fail ? "sphere_check: FAILED\n" : "sphere_check: all checks passed\n");
+    return fail;
+}

@@ -18,3 +18,13 @@ def test_cpp_header_shim(gpu):
     r = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+def test_cpp_sphere_c5(gpu):
+    """differentiable ray-sphere render, forward + backward, CPU reference tape vs this backend."""
+    binp = os.path.join(os.path.dirname(BIN), "sphere_check")
+    if not os.path.exists(binp):
+        pytest.skip("tests/cpp/sphere_check not built (needs the reference headers at build time)")
+    r = subprocess.run([binp, "512"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
