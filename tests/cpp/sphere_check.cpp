@@ -90,9 +90,13 @@ int main(int argc, char **argv) {
     printf("sphere_check: %zux%zu rays  image max|diff| = %.3g (%zu px > 2e-6)\n", res, res, maxd, bad);
     printf("  loss cpu %.8g  gpu %.8g\n", loss_c, loss_g);
     if (std::fabs(loss_c - loss_g) > 1e-5 * std::fabs(loss_c)) fail = 1;
+    float gmax = 0;
+    for (int k = 0; k < 6; ++k) gmax = std::max(gmax, std::fabs(gc[k]));
     for (int k = 0; k < 6; ++k) {
         printf("  grad[%d] cpu % .8g  gpu % .8g\n", k, gc[k], gg[k]);
-        if (std::fabs(gc[k] - gg[k]) > 2e-4 * std::max(1e-3f, std::fabs(gc[k]))) fail = 1;
+        /* the six gradients are sums of n terms with cancellation (d/d delta_z is analytically 0): compare against
+           the largest gradient magnitude (float reductions are reassociated, SURVEY 7 hard part 4) */
+        if (std::fabs(gc[k] - gg[k]) > 2e-5 * gmax) fail = 1;
     }
     printf("  time: cpu %.1f ms, gpu first %.1f ms, gpu second %.1f ms\n",
            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
