@@ -343,6 +343,11 @@ def main():
         for p in hb:
             L.ek_host_free(p)
 
+    # ---- C3 (configs[2]): 2^26-sample gather + scatter_add histogram, kernel-only time
+    hist = None
+    if rank == 0:
+        hist = bench_histogram(ek, L, n, peak_gbs)
+
     # ---- backward: C4 tape (per rank), K' passes of backward(free_graph=False)
     backward = None
     if not args.skip_backward:
@@ -368,12 +373,50 @@ def main():
                        "l2": "inputs 4 x 256 MiB per step exceed the 126 MB L2 (no explicit flush needed)",
                        "parallelism": f"element-range sharding x{world}, one rank per GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "backward": backward, "wall_ms_per_step": wall_ms / args.steps, "loss_checksum": loss_val,
+            "backward": backward, "histogram": hist, "wall_ms_per_step": wall_ms / args.steps, "loss_checksum": loss_val,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_histogram(ek, L, n, peak_gbs):
+    """SURVEY 8d C3: samples resident in HBM; idx = UInt32((y+4)*31/8); mask = idx<31; w = gather(table31, idx, mask);
+    scatter_add(bins_u32, 1, idx, mask); scatter_add(hist_f32, w, idx, mask).  Algorithmic bytes: 4 B / sample."""
+    from enoki_b200 import Float32, UInt32, fmadd, gather, scatter_add
+    i = UInt32.arange(n)
+    h = i * np.uint32(2654435761) + np.uint32(974711)
+    h = (h ^ (h >> 15)) * np.uint32(2246822519)
+    y = fmadd(Float32(h >> 8), Float32(8.2 / (1 << 24)), Float32(-4.1))
+    ek.cuda_eval(); del i, h
+    table = Float32.copy(np.linspace(0.5, 1.5, 31, dtype=np.float32))
+    table.eval()
+
+    def one():
+        idx = UInt32((y - (-4.0)) * 31.0 / 8.0)
+        mask = idx < UInt32(31)
+        w = gather(Float32, table, idx, mask)
+        bins = UInt32.zero(31); hist = Float32.zero(31)
+        scatter_add(bins, UInt32(1), idx, mask)
+        scatter_add(hist, w, idx, mask)
+        del idx, mask, w
+        ek.cuda_eval()
+        return bins, hist
+    for _ in range(3):
+        one()
+    L.ek_set_timing(1); L.ek_stats_reset()
+    reps = 5
+    for _ in range(reps):
+        b, _h = one()
+    st = ek.stats()
+    L.ek_set_timing(0)
+    ms = st.total_kernel_ms / max(int(st.sweep_launches), 1)
+    total = int(b.numpy().astype(np.uint64).sum())
+    return {"workload": "C3: 2^26-sample gather(31-entry table) + scatter_add(31 u32 bins, 31 f32 bins)", "kernel_ms": ms,
+            "m_samples_per_s": n / (ms * 1e-3) / 1e6, "in_range": total,
+            "roofline": {"bound": "hbm", "achieved": 4.0 * n / (ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": 4.0 * n / (ms * 1e-3) / 1e9 / peak_gbs, "bytes_per_sample": 4.0}}
 
 
 def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):

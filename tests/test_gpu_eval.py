@@ -386,3 +386,31 @@ def test_psum_compress_raw(gpu):
     assert osz.value == int(mask.sum())
     got = ek.UInt32.map(od.value, osz.value, True).numpy()
     assert (got == u[mask]).all()
+
+
+def test_histogram_full_size_properties(gpu):
+    """C3 at BASELINE size (2^26 samples): gather from a 31-entry table + scatter_add into 31 uint32 / float bins.
+    Size-independent properties: the integer bins equal numpy's bincount of the device-computed indices (bit-exact),
+    their sum equals the number of in-range samples, the float histogram equals sum(table[idx]) within 1e-5."""
+    ek = gpu
+    n = 1 << 26
+    i = ek.UInt32.arange(n)
+    h = i * np.uint32(2654435761) + np.uint32(974711)
+    h = (h ^ (h >> 15)) * np.uint32(2246822519)
+    y = ek.fmadd(ek.Float32(h >> 8), ek.Float32(8.2 / (1 << 24)), ek.Float32(-4.1))     # U(-4.1, 4.1): some out of range
+    ek.cuda_eval()
+    table = np.linspace(0.5, 1.5, 31, dtype=np.float32)
+    T = ek.Float32.copy(table)
+    idx = ek.UInt32((y - (-4.0)) * 31.0 / 8.0)
+    mask = idx < ek.UInt32(31)
+    w = ek.gather(ek.Float32, T, idx, mask)
+    bins = ek.UInt32.zero(31); hist = ek.Float32.zero(31)
+    ek.scatter_add(bins, ek.UInt32(1), idx, mask)
+    ek.scatter_add(hist, w, idx, mask)
+    got_bins = bins.numpy(); got_hist = hist.numpy(); hidx = idx.numpy()
+    inr = hidx < 31
+    want = np.bincount(hidx[inr], minlength=31).astype(np.uint32)
+    assert (got_bins == want).all()
+    assert int(got_bins.sum()) == int(inr.sum()) and 0 < int((~inr).sum()) < n // 20
+    truth = want.astype(np.float64) * table.astype(np.float64)
+    assert np.allclose(got_hist, truth, rtol=1e-5)
