@@ -546,10 +546,19 @@ struct Assembler {
             set_b_code(ini, w64 ? uni_lit(lit_pair(ident)) : uni_lit(lit_word((uint32_t) ident)), w64);
             ini.flags |= EKF_ST | (w64 ? EKF_R64 : 0); ini.dst = (uint16_t) acc;
             out.init.push_back(ini);
-            ensure_acc(d0);
-            EkInstr in = mk(DOP_RACC, (uint32_t) kind | ((uint32_t) cls << 8));
-            in.dst = (uint16_t) acc;
-            push_body(in);
+            EkInstr *last = out.body.empty() ? nullptr : &out.body.back();
+            if (acc_var == d0 && !pending_a && !pending_mod && last && last_emitted_for == d0 &&
+                !(last->flags & (EKF_ST | EKF_HAS_A | EKF_RACC))) {
+                /* fused into the instruction that produces the value */
+                last->flags |= EKF_RACC;
+                last->dst = (uint16_t) acc;
+                last->a = (uint16_t) ((uint32_t) kind | ((uint32_t) cls << 8));
+            } else {
+                ensure_acc(d0);
+                EkInstr in = mk(DOP_RACC, (uint32_t) kind | ((uint32_t) cls << 8));
+                in.dst = (uint16_t) acc;
+                push_body(in);
+            }
             uint32_t pa = arg_ptr(idx, true);
             out.outputs.push_back({ idx, pa, 8 });
             EkInstr fi = mk(DOP_RFIN, (uint32_t) kind | ((uint32_t) cls << 8) | (ridx << 16));
@@ -822,7 +831,8 @@ struct Assembler {
        it to a scratch slot first */
     void ensure_slot_or_alias(EkInstr &ins, uint32_t vv, bool as_b) {
         auto l = loc.find(vv);
-        if (l == loc.end() || l->second.kind != Loc::SLOT) {
+        bool resident = l != loc.end() && (l->second.kind == Loc::SLOT || l->second.kind == Loc::STAGED || l->second.kind == Loc::UNI);
+        if (!resident) {
             bool is64 = ek_is_64(var(vv).type);
             uint32_t s = alloc_slots(is64 ? 2 : 1);
             EkInstr sp = mk(DOP_NOP);
@@ -934,7 +944,7 @@ struct Assembler {
         auto fix = [&](std::vector<EkInstr> &v) {
             for (EkInstr &in : v) {
                 in.b = rebase_code(in.b); in.c = rebase_code(in.c);
-                in.a = rebase_code(in.a);
+                if (in.flags & EKF_HAS_A) in.a = rebase_code(in.a);
                 uint32_t mark = (in.flags >> 12) & 3u;
                 in.flags &= ~0x3000u;
                 if (mark == 3) {                    /* gather/scatter: low 16 bits = uniform code of pointer */
@@ -1201,6 +1211,7 @@ void dump_program(std::ostream &os, const Assembled &a, const Group &g) {
             if (in.flags & EKF_ABS_A) os << " abs";
             os << " b=" << opnd_str(in.b) << " c=" << opnd_str(in.c);
             if (in.flags & EKF_STG) os << " stg";
+            if (in.flags & EKF_RACC) os << " racc->s" << in.dst;
             if (in.flags & EKF_REL) os << " rel";
             if (in.flags & EKF_ST) os << " -> s" << in.dst;
             os << " imm=0x" << std::hex << in.imm << std::dec << "\n";
@@ -1306,8 +1317,9 @@ static int eval_impl(bool dry, std::string *dump) {
             };
             auto patch_all = [&](std::vector<EkInstr> &v) {
                 for (EkInstr &in : v) {
-                    in.b = patch(in.b); in.c = patch(in.c); in.a = patch(in.a);
-                    if ((in.flags & EKF_ST) || in.op == DOP_RACC) in.dst = patch(in.dst);
+                    in.b = patch(in.b); in.c = patch(in.c);
+                    if (in.flags & EKF_HAS_A) in.a = patch(in.a);
+                    if ((in.flags & (EKF_ST | EKF_RACC)) || in.op == DOP_RACC) in.dst = patch(in.dst);
                 }
             };
             patch_all(a.init); patch_all(a.body); patch_all(a.fini);

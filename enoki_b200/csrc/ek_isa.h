@@ -44,6 +44,8 @@ struct EkInstr {
 #define EKF_ABS_A 0x0200u   /* f32 input modifier: accumulator = |accumulator|                */
 #define EKF_REL   0x0800u   /* after executing: the staged inputs in args.release_mask are dead for this tile --
                                start streaming them for the CTA's next tile (single-buffered pipelines)   */
+#define EKF_RACC  0x4000u   /* after executing: fold the accumulator into the reduction partials in slot dst
+                               (kind | class << 8 in field `a`; only when EKF_ST and EKF_HAS_A are clear)   */
 #define EKF_STG   0x0400u   /* after executing, store the 32-bit accumulator to the global array
                                whose pointer is the uniform pair at index imm                 */
 
