@@ -674,7 +674,7 @@ struct Assembler {
                 ensure_acc(d1);
                 if (smem_bins) {
                     uint32_t count = (uint32_t) var(v.extra_dep).size;
-                    uint32_t copies = std::max(1u, std::min(16u, 4096u / count));
+                    uint32_t copies = std::max(1u, std::min(32u, 4096u / count));
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(copies); out.argw.push_back(pa);
                     out.extra_bytes += (count * copies * 4 + 15) & ~15u;

@@ -413,4 +413,5 @@ def test_histogram_full_size_properties(gpu):
     assert (got_bins == want).all()
     assert int(got_bins.sum()) == int(inr.sum()) and 0 < int((~inr).sum()) < n // 20
     truth = want.astype(np.float64) * table.astype(np.float64)
-    assert np.allclose(got_hist, truth, rtol=1e-5)
+    # ~2 M fp32 terms per bin: atomics reassociate the sum; 1e-4 relative (a sequential fp32 CPU sum is worse)
+    assert np.allclose(got_hist, truth, rtol=1e-4)
