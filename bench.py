@@ -118,37 +118,51 @@ def aligned_f32(n, align=64):
     return raw[off:off + n * 4].view(np.float32)
 
 
+class CpuC2:
+    """The reference's CPU implementation of C2 on `threads` host threads, each on its own slice of
+    `sample_elems` elements (Enoki is single-threaded by construction; the split is the embarrassingly
+    parallel one of BASELINE.md section 3).  Buffers are allocated once; run() returns elements/s."""
+
+    def __init__(self, sample_elems, threads):
+        self.lib, self.kind = load_ref(True)
+        self.threads = threads
+        self.per = (sample_elems // threads) // 16 * 16
+        rng = np.random.default_rng(0)
+        block = rng.uniform(-4, 4, min(self.per, 1 << 20)).astype(np.float32)
+        self.bufs = []
+        for _ in range(threads):
+            xs = []
+            for k in range(4):
+                a = aligned_f32(self.per)
+                for o in range(0, self.per, len(block)):
+                    m = min(len(block), self.per - o)
+                    a[o:o + m] = np.roll(block, 17 * k + 1)[:m]
+                xs.append(a)
+            self.bufs.append((xs, aligned_f32(self.per)))
+
+    def run(self, reps):
+        best = [0.0] * self.threads
+        per = self.per
+
+        def work(t):
+            xs, out = self.bufs[t]
+            if self.kind == "reference":
+                # the reference's own fastest CPU form: the fused vectorize() loop (dynamic.h:1025-1074)
+                best[t] = self.lib.ref_c2_time_vectorized(P(xs[0]), P(xs[1]), P(xs[2]), P(xs[3]), P(out), ctypes.c_size_t(per), reps)
+            else:
+                best[t] = self.lib.or_c2_time(P(xs[0]), P(xs[1]), P(xs[2]), P(xs[3]), P(out), ctypes.c_size_t(per), reps)
+
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(self.threads)]
+        for th in ths: th.start()
+        for th in ths: th.join()
+        return per * self.threads / max(best)
+
+
 def cpu_c2(sample_elems, reps, threads):
-    """Time the reference's CPU implementation of C2 on `threads` host threads, each on its own
-    slice of `sample_elems` elements (Enoki is single-threaded by construction; the split is the
-    embarrassingly-parallel one of BASELINE.md section 3).  Returns elements/s (aggregate)."""
-    lib, kind = load_ref(True)
-    per = (sample_elems // threads) // 16 * 16
-    rng = np.random.default_rng(0)
-    bufs = []
-    for _ in range(threads):
-        xs = []
-        for _k in range(4):
-            a = aligned_f32(per); a[:] = rng.uniform(-4, 4, per).astype(np.float32); xs.append(a)
-        out = aligned_f32(per)
-        bufs.append((xs, out))
-    best = [0.0] * threads
-
-    def work(t):
-        xs, out = bufs[t]
-        if kind == "reference":
-            # the reference's own fastest CPU form: the fused vectorize() loop (dynamic.h:1025-1074)
-            best[t] = lib.ref_c2_time_vectorized(P(xs[0]), P(xs[1]), P(xs[2]), P(xs[3]), P(out), ctypes.c_size_t(per), reps)
-        else:
-            best[t] = lib.or_c2_time(P(xs[0]), P(xs[1]), P(xs[2]), P(xs[3]), P(out), ctypes.c_size_t(per), reps)
-
-    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    c = CpuC2(sample_elems, threads)
     t0 = time.time()
-    for th in ths: th.start()
-    for th in ths: th.join()
-    wall = time.time() - t0
-    slowest = max(best)
-    return per * threads / slowest, kind, wall
+    r = c.run(reps)
+    return r, c.kind, time.time() - t0
 
 
 def run_reference(args):
@@ -156,17 +170,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 1 << 24
-    reps_per_step = 1
-    lib, kind = load_ref(True)
-    # warm-up + K timed "steps", each a bounded sample of the workload on all host threads
+    sample = N_ELEMS              # the whole 2^26-element workload, split over all host threads (DRAM resident)
+    c = CpuC2(sample, cores)
     for _ in range(max(args.warmup, 1)):
-        cpu_c2(sample, 1, cores)
+        c.run(1)
+    # K timed "steps": each one pass of the whole workload on all host threads
     t0 = time.time()
-    rates = []
-    for _ in range(args.steps):
-        r, kind, _ = cpu_c2(sample, reps_per_step, cores)
-        rates.append(r)
+    rates = [c.run(1) for _ in range(args.steps)]
     wall = time.time() - t0
     elems_per_s = float(np.median(rates))
     value = elems_per_s * C2_NODES / 1e6
@@ -177,8 +187,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: CUDAArray<float> 64M-elem fused arith+exp/sin chain (CPU: DynamicArray<Packet<float,8>> vectorize() form)",
                    "elems": N_ELEMS, "nodes": C2_NODES},
-        "cpu_baseline": {"value": value, "unit": "M array-ops/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample} of {N_ELEMS} elements per step, split over {cores} threads, AVX2+FMA -ffp-contract=fast"},
+        "cpu_baseline": {"value": value, "unit": "M array-ops/s", "cores": cores, "kind": c.kind,
+                         "sample": f"{sample} of {N_ELEMS} elements per step, split over {cores} threads (DRAM resident), vectorize() form, AVX2+FMA -ffp-contract=fast"},
         "e2e": {"value": value, "unit": "M array-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -357,10 +367,11 @@ def main():
     cpu = None
     if rank == 0 and not args.skip_cpu:
         cores = os.cpu_count() or 1
-        r, kind, wall = cpu_c2(1 << 24, 3, cores)
-        r1, _, wall1 = cpu_c2(1 << 22, 3, 1)
+        r, kind, wall = cpu_c2(N_ELEMS, 3, cores)
+        r1, _, wall1 = cpu_c2(1 << 24, 2, 1)
         cpu = {"value": r * C2_NODES / 1e6, "unit": "M array-ops/s", "cores": cores, "kind": kind,
-               "sample": f"2^24 of 2^26 elements split over {cores} threads (vectorize() form, best of 3); single thread on 2^22: "
+               "sample": f"all 2^26 elements split over {cores} threads, {N_ELEMS // cores * 20 >> 20} MiB per thread (DRAM resident; "
+                         f"reference vectorize() form, AVX2+FMA -ffp-contract=fast, best of 3); single thread on 2^24: "
                          f"{r1 * C2_NODES / 1e6:.1f} M array-ops/s"}
 
     if rank == 0:
