@@ -216,6 +216,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("EK_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
     import torch
     dist = None
     if world > 1:

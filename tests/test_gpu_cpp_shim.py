@@ -28,3 +28,14 @@ def test_cpp_sphere_c5(gpu):
     r = subprocess.run([binp, "512"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+def test_cpp_autodiff_parity(gpu):
+    """Appendix-B op list, special edges (gather/scatter/scatter_add/psum/reverse), forward mode: the same templates
+    on the reference CPU tape and on this backend; plus the reference tests' published expected vectors."""
+    binp = os.path.join(os.path.dirname(BIN), "autodiff_check")
+    if not os.path.exists(binp):
+        pytest.skip("tests/cpp/autodiff_check not built (needs the reference headers at build time)")
+    r = subprocess.run([binp], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
