@@ -448,8 +448,10 @@ int backward_impl(Tape &T, bool free_graph) {
                 if ((ws != 1 && ws != s.size) || (gs != 1 && gs != s.size)) { simple = false; break; }
                 if (t.grad) {
                     uint64_t bits;
-                    if (ctx.vars[t.grad].data == nullptr && !var_imm(t.grad, bits)) {
-                        /* adjoint produced by the generic path and still an unevaluated trace */
+                    const EkVariable &gv = ctx.vars[t.grad];
+                    if ((gv.data == nullptr && !var_imm(t.grad, bits)) || gv.dirty) {
+                        /* adjoint produced by the generic path: still an unevaluated trace, or a buffer with
+                           pending scatter_add side effects (gather edges) */
                         if (ek_eval() != 0) return -1;
                     }
                 }
