@@ -438,6 +438,7 @@ def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
     out-edge (10.0 B / edge-adjoint).  Timed: backward() only (the tape is built once)."""
     from enoki_b200 import Float32, UInt32, fmadd, select
     F32 = ek.EK_FLOAT32
+    L.ek_tape_set_graph_simplification(F32, 0)      # C4 is defined on materialised weights (SURVEY 8d)
     Lv, K, w = C4["levels"], C4["per_level"], C4["width"]
     rng = np.random.default_rng(1234 + rank)
     idx = UInt32.arange(w)

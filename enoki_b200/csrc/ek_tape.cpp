@@ -70,12 +70,30 @@ struct Tape {
 
 Tape *g_tapes[2] = { nullptr, nullptr };
 
+int simplify_graph(Tape &T);
+
+/* autodiff.cpp:248-252: the tape simplifies itself right before every cuda_eval() */
+void tape_eval_callback(void *p) {
+    Tape *T = (Tape *) p;
+    if (T->graph_simplification) simplify_graph(*T);
+}
+
 Tape *tape_of(ek_type t) {
     int i = t == EK_FLOAT64 ? 1 : 0;
     if (t != EK_FLOAT32 && t != EK_FLOAT64) { ek_set_error("tape: value type must be Float32 or Float64"); return nullptr; }
-    if (!g_tapes[i]) { g_tapes[i] = new Tape(); g_tapes[i]->vt = t; }
+    if (!g_tapes[i]) {
+        g_tapes[i] = new Tape(); g_tapes[i]->vt = t;
+        ek_register_callback(tape_eval_callback, g_tapes[i]);      /* autodiff.cpp:214-221 */
+    }
     return g_tapes[i];
 }
+
+/* RAII equivalent of the reference's SimplificationLock (autodiff.cpp:194-205) */
+struct SimplifyLock {
+    Tape &T; bool saved;
+    explicit SimplifyLock(Tape &t) : T(t), saved(t.graph_simplification) { T.graph_simplification = false; }
+    ~SimplifyLock() { T.graph_simplification = saved; }
+};
 
 TNode *node(Tape &T, uint32_t idx) {
     auto it = T.nodes.find(idx);
@@ -641,6 +659,89 @@ int forward_impl(Tape &T, bool free_graph) {
     return 0;
 }
 
+/* Greedy vertex elimination, behavioural spec autodiff.cpp:990-1074 (+ append_edge_prod :645-679):
+   repeatedly collapse the interior node with the smallest in-degree x out-degree product (while that
+   cost is <= 10): every (in-edge, out-edge) pair becomes one edge whose weight is the zero-guarded
+   product of the two weights (added to an existing parallel edge with a zero-guarded fma).  Nodes
+   touching special edges, and size-1 nodes fed by wide nodes, are left alone.  The new weights are
+   ordinary trace expressions: they are fused into the next sweep and the collapsed node's own weight
+   arrays are never materialised. */
+int simplify_graph(Tape &T) {
+    if (T.is_simplified) return 0;
+    SimplifyLock lock(T);
+    const uint32_t max_cost = 10;                       /* ENOKI_AUTODIFF_MAX_SIMPLIFICATION_COST */
+    auto score = [](const TNode &n) { return (uint32_t) (n.edges.size() * n.edges_rev.size()); };
+    std::set<std::pair<uint32_t, uint32_t>> todo;
+    for (auto &kv : T.nodes) todo.emplace(score(kv.second), kv.first);
+    std::vector<std::pair<uint32_t, uint32_t>> update;
+
+    while (!todo.empty()) {
+        auto it = todo.begin();
+        uint32_t sc = it->first, index = it->second;
+        todo.erase(it);
+        auto nit = T.nodes.find(index);
+        if (nit == T.nodes.end()) continue;
+        TNode &n = nit->second;
+        if (n.edges.empty() || n.edges_rev.empty()) continue;           /* collapse_allowed() */
+        if (sc > max_cost) break;
+
+        update.clear();
+        bool skip = false;
+        for (uint32_t k : n.edges_rev) {
+            TNode *c = node(T, k); if (!c) return -1;
+            for (const TEdge &e : c->edges) if (e.source == index && e.special) skip = true;
+            update.emplace_back(score(*c), k);
+        }
+        for (const TEdge &e : n.edges) {
+            TNode *src = node(T, e.source); if (!src) return -1;
+            update.emplace_back(score(*src), e.source);
+            if ((n.size == 1 && src->size != n.size) || e.special) skip = true;
+        }
+        if (skip) continue;
+
+        std::vector<uint32_t> consumers = n.edges_rev;
+        for (uint32_t other : consumers) {
+            TNode &o = *node(T, other);
+            /* detach the edge index -> other */
+            TEdge edge1;
+            bool found = false;
+            for (auto eit = o.edges.begin(); eit != o.edges.end(); ++eit)
+                if (eit->source == index && !eit->special) { edge1 = *eit; o.edges.erase(eit); found = true; break; }
+            if (!found) { ek_set_error("simplify_graph(): internal error -- edge not found"); return -1; }
+            for (const TEdge &edge2 : n.edges) {
+                /* append_edge_prod(edge2.source, other, edge1.weight, edge2.weight) */
+                TEdge *ex = nullptr;
+                for (TEdge &e : o.edges) if (e.source == edge2.source && !e.special) { ex = &e; break; }
+                if (ex) {
+                    uint32_t w = v_op(T.vt, EK_OP_FMA_NZ, edge1.weight, edge2.weight, ex->weight);
+                    if (!w) return -1;
+                    ek_dec_ref_ext(ex->weight);
+                    ex->weight = w;
+                } else {
+                    uint32_t w = v_op(T.vt, EK_OP_MUL_NZ, edge1.weight, edge2.weight);
+                    if (!w) return -1;
+                    TEdge ne; ne.source = edge2.source; ne.weight = w;      /* takes the ext ref of w */
+                    o.edges.push_back(ne);
+                    inc_ref_int(T, edge2.source, other);
+                }
+            }
+            release_edge(edge1);
+            dec_ref_int(T, index, other);          /* may free `index` (and cascade) once its last consumer is gone */
+        }
+
+        for (auto &u : update) {
+            auto f = todo.find(u);
+            if (f == todo.end()) continue;
+            auto un = T.nodes.find(u.second);
+            if (un == T.nodes.end()) { todo.erase(f); continue; }
+            uint32_t ns = score(un->second);
+            if (ns != u.first) { todo.erase(f); todo.emplace(ns, u.second); }
+        }
+    }
+    T.is_simplified = true;
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -696,6 +797,7 @@ uint32_t ek_tape_append_gather(ek_type t, uint32_t offset_var, uint32_t mask_var
 int ek_tape_append_scatter(ek_type t, uint32_t source, uint32_t offset_var, uint32_t mask_var, int scatter_add) {
     Tape *T = tape_of(t); if (!T) return -1;
     if (T->sg_index == nullptr || source == 0) return 0;
+    SimplifyLock lock(*T);                                  /* autodiff.cpp:526 */
     uint32_t target_orig = *T->sg_index;
     Special *sp = new Special();
     sp->kind = SP_SCATTER; sp->offset = offset_var; sp->mask = mask_var;
@@ -789,24 +891,23 @@ int ek_tape_set_gradient(ek_type t, uint32_t index, uint32_t value_var, int back
 
 int ek_tape_backward_static(ek_type t, int free_graph) {
     Tape *T = tape_of(t); if (!T) return -1;
-    bool saved = T->graph_simplification; T->graph_simplification = false;
+    SimplifyLock lock(*T);
     int rc = backward_impl(*T, free_graph != 0);
-    T->graph_simplification = saved;
     if (rc != 0) T->scheduled.clear();
     return rc;
 }
 
 int ek_tape_forward_static(ek_type t, int free_graph) {
     Tape *T = tape_of(t); if (!T) return -1;
-    bool saved = T->graph_simplification; T->graph_simplification = false;
+    SimplifyLock lock(*T);
     int rc = forward_impl(*T, free_graph != 0);
-    T->graph_simplification = saved;
     if (rc != 0) T->scheduled.clear();
     return rc;
 }
 
 int ek_tape_backward(ek_type t, uint32_t index, int free_graph) {
     Tape *T = tape_of(t); if (!T) return -1;
+    SimplifyLock lock(*T);                                  /* autodiff.cpp:808 */
     uint32_t one = v_literal(t, 1.0);
     int rc = ek_tape_set_gradient(t, index, one, 1);
     ek_dec_ref_ext(one);
@@ -816,6 +917,7 @@ int ek_tape_backward(ek_type t, uint32_t index, int free_graph) {
 
 int ek_tape_forward(ek_type t, uint32_t index, int free_graph) {
     Tape *T = tape_of(t); if (!T) return -1;
+    SimplifyLock lock(*T);                                  /* autodiff.cpp:817 */
     uint32_t one = v_literal(t, 1.0);
     int rc = ek_tape_set_gradient(t, index, one, 0);
     ek_dec_ref_ext(one);
@@ -855,10 +957,7 @@ void ek_tape_set_graph_simplification(ek_type t, int enable) { Tape *T = tape_of
 
 int ek_tape_simplify(ek_type t) {
     Tape *T = tape_of(t); if (!T) return -1;
-    /* greedy vertex elimination (autodiff.cpp:990-1074) is a "next" row of SURVEY 8f; the
-       level-batched backward pass does not depend on it for correctness */
-    T->is_simplified = true;
-    return 0;
+    return simplify_graph(*T);
 }
 
 char *ek_tape_graphviz(ek_type t, size_t n, const uint32_t *indices) {

@@ -164,6 +164,7 @@ int main() {
             maxd = std::max(maxd, d);
         }
         printf("%-16s %s  n=%zu/%zu  max rel diff %.3g\n", c.name, ok ? "ok  " : "FAIL", a.size(), b.size(), maxd);
+        if (!ok) for (size_t i = 0; i < std::min(a.size(), b.size()); ++i) printf("    [%zu] cpu % .9g  gpu % .9g\n", i, a[i], b[i]);
         if (!ok) ++failures;
     }
     /* published expected vectors of the reference's own tests (tests/autodiff.cpp:414-430,620-635) */

@@ -35,6 +35,17 @@ def build_tape(ek, g):
 
 def run_backward(ek, g):
     L = ek.lib()
+    # the CPU reference tape never simplifies (the pre-eval callback exists for CUDA arrays only,
+    # autodiff.cpp:214-221): bit-exact comparisons need the unsimplified graph
+    L.ek_tape_set_graph_simplification(F32, 0)
+    try:
+        return _run_backward(ek, g)
+    finally:
+        L.ek_tape_set_graph_simplification(F32, 1)
+
+
+def _run_backward(ek, g):
+    L = ek.lib()
     ids, keep = build_tape(ek, g)
     assert L.ek_tape_backward(F32, ids[int(g["root"])], 1) == 0, L.ek_last_error()
     outs = []
@@ -152,3 +163,36 @@ def test_gradient_descent(gpu):
         x = ad.FloatD(nv)
     final = float(x.value.numpy()[0])
     assert abs(final - (1 + 2 * 0.8 ** 10)) < 1e-5
+
+
+def test_simplify_graph_preserves_gradients(gpu):
+    """Greedy vertex elimination (autodiff.cpp:990-1074) collapses interior nodes into zero-guarded weight
+    products; gradients must be unchanged (up to reassociation of the products)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden import make_tape
+    ek = gpu
+    L = ek.lib()
+    g = make_tape(np.random.default_rng(3), 5, 6, 257, zero_frac=0.02)
+    L.ek_tape_set_graph_simplification(F32, 0)
+    a = _run_backward(ek, g)
+    ids, keep = build_tape(ek, g)
+    n_before = L.ek_tape_node_count(F32)
+    L.ek_tape_set_graph_simplification(F32, 1)
+    for i in ids[1:]:
+        if i not in (ids[int(g["root"])],) and i not in [ids[int(w)] for w in g["want"]]:
+            L.ek_tape_dec_ref_ext(F32, i)            # interior nodes are only referenced by the graph
+    assert L.ek_tape_simplify(F32) == 0
+    assert L.ek_tape_node_count(F32) < n_before       # interior nodes with degree product <= 10 are gone
+    assert L.ek_tape_backward(F32, ids[int(g["root"])], 1) == 0, L.ek_last_error()
+    outs = []
+    for wnt in g["want"]:
+        h = L.ek_tape_gradient(F32, ids[int(wnt)])
+        L.ek_inc_ref_ext(h)
+        outs.append(ek.Float32.from_index(h).numpy())
+    b = np.concatenate(outs)
+    for wnt in g["want"]:
+        L.ek_tape_dec_ref_ext(F32, ids[int(wnt)])
+    L.ek_tape_dec_ref_ext(F32, ids[int(g["root"])])
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert L.ek_tape_node_count(F32) == 0
