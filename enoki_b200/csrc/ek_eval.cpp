@@ -558,6 +558,7 @@ struct Assembler {
                 EkInstr in = mk(DOP_RACC, (uint32_t) kind | ((uint32_t) cls << 8));
                 in.dst = (uint16_t) acc;
                 push_body(in);
+                last_emitted_for = 0;        /* the last instruction is no longer the producer of d0 */
             }
             uint32_t pa = arg_ptr(idx, true);
             out.outputs.push_back({ idx, pa, 8 });
