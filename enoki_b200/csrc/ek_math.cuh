@@ -118,6 +118,111 @@ __device__ __forceinline__ float log_f32(float x) {
     return valid ? r : fbits(0xffffffffu);
 }
 
+/* ---------------- double precision (array_math.h, the `!Single` branches) ---------------- */
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ double dbits(uint64_t u) { return __longlong_as_double((long long) u); }
+__device__ __forceinline__ uint64_t ubits(double d) { return (uint64_t) __double_as_longlong(d); }
+/* x86 cvttpd2qq / scalar cvttsd2si semantics */
+__device__ __forceinline__ long long cvtt_f64_i64(double x) {
+    return (x >= -9223372036854775808.0 && x < 9223372036854775808.0) ? __double2ll_rz(x) : (long long) 0x8000000000000000ull;
+}
+__device__ __forceinline__ double poly2(double x, double c0, double c1, double c2) {
+    double x2 = dmul(x, x);
+    return dfma(x2, c2, dfma(x, c1, c0));
+}
+__device__ __forceinline__ double poly3(double x, double c0, double c1, double c2, double c3) {
+    double x2 = dmul(x, x);
+    return dfma(x2, dfma(x, c3, c2), dfma(x, c1, c0));
+}
+__device__ __forceinline__ double poly5(double x, double c0, double c1, double c2, double c3, double c4, double c5) {
+    double x2 = dmul(x, x), x4 = dmul(x2, x2);
+    return dfma(x2, dfma(x, c3, c2), dfma(x4, dfma(x, c5, c4), dfma(x, c1, c0)));
+}
+
+/* array_math.h:261-367 sincos_approx, double branch */
+template <bool Sin, bool Cos>
+__device__ __forceinline__ void sincos(double x, double &s_out, double &c_out) {
+    double xa = fabs(x);
+    long long j = cvtt_f64_i64(dmul(xa, 1.2732395447351626862));
+    j = (j + 1) & 0xfffffffell;   /* the reference masks with Int(~1u): a 32-bit constant widened to 64 */
+    double y = __ll2double_rn(j);
+    uint64_t sign_sin = ((uint64_t) j << 61) ^ ubits(x);
+    uint64_t sign_cos = (uint64_t) (~(j - 2)) << 61;
+    y = dsub(dsub(dsub(xa, dmul(y, 7.85398125648498535156e-1)), dmul(y, 3.77489470793079817668e-8)),
+             dmul(y, 2.69515142907905952645e-15));
+    double z = dmul(y, y);
+    if (xa == dbits(0x7ff0000000000000ull)) z = dbits(~0ull);
+    double s = dmul(poly5(z, -1.66666666666666307295e-1, 8.33333333332211858878e-3, -1.98412698295895385996e-4,
+                             2.75573136213857245213e-6, -2.50507477628578072866e-8, 1.58962301576546568060e-10), z);
+    double c = dmul(poly5(z, 4.16666666666665929218e-2, -1.38888888888730564116e-3, 2.48015872888517045348e-5,
+                             -2.75573141792967388112e-7, 2.08757008419747316778e-9, -1.13585365213876817300e-11), z);
+    s = dfma(s, y, y);
+    c = dfma(c, z, dfma(z, -0.5, 1.0));
+    bool polymask = (j & 2) == 0;
+    if (Sin) s_out = dbits(ubits(polymask ? s : c) ^ (sign_sin & 0x8000000000000000ull));
+    if (Cos) c_out = dbits(ubits(polymask ? c : s) ^ (sign_cos & 0x8000000000000000ull));
+}
+__device__ __forceinline__ double sin_f64(double x) { double s, c; sincos<true, false>(x, s, c); return s; }
+__device__ __forceinline__ double cos_f64(double x) { double s, c; sincos<false, true>(x, s, c); return c; }
+
+/* array_math.h:711-776 exp, double branch */
+__device__ __forceinline__ double exp_f64(double x) {
+    const double max_range = +7.0943613930310391424428e2, min_range = -7.0943613930310391424428e2;
+    bool overflow = x > max_range, underflow = x < min_range;
+    double n = floor(dfma(1.4426950408889634073599, x, 0.5));
+    double xr = dfma(-n, 6.93145751953125e-1, x);
+    xr = dfma(-n, 1.42860682030941723212e-6, xr);
+    double z = dmul(xr, xr);
+    double p = dmul(poly2(z, 9.99999999999999999910e-1, 3.02994407707441961300e-2, 1.26177193074810590878e-4), xr);
+    double q = poly3(z, 2.00000000000000000009e0, 2.27265548208155028766e-1, 2.52448340349684104192e-3, 3.00198505138664455042e-6);
+    double pq = __ddiv_rn(p, dsub(q, p));
+    z = dadd(dadd(pq, pq), 1.0);
+    uint64_t scale = (uint64_t) (cvtt_f64_i64(n) + 0x3ff) << 52;
+    double r = dmul(z, dbits(scale));
+    return overflow ? dbits(0x7ff0000000000000ull) : (underflow ? 0.0 : r);
+}
+
+/* array_math.h:778-898 log, double branch (both sub-branches evaluated and selected, as the IsCuda path does) */
+__device__ __forceinline__ double log_f64(double x) {
+    bool valid = x >= 0.0;
+    uint64_t xi = ubits(x);
+    uint64_t exponent_bits = xi & 0x7ff0000000000000ull;
+    bool is_normal = (x != 0.0) && (exponent_bits != 0x7ff0000000000000ull);
+    long long exponent_i = (long long) (exponent_bits >> 52) - 0x3ff;
+    uint64_t mantissa = (xi & ~0x7ff0000000000000ull) | 0x3fe0000000000000ull;
+    double xm = dbits(is_normal ? mantissa : xi);
+    double e = __ll2double_rn(is_normal ? exponent_i : 0);
+    bool e_big = fabs(e) > 2.0;
+    bool ge = xm >= 0.70710678118654752440;
+    if (ge) e = dadd(e, 1.0);
+    /* big exponent: log(x) = z + z^3 P(z)/Q(z), z = 2(x-1)/(x+1) */
+    double zb = dsub(xm, 0.5);
+    if (ge) zb = dsub(zb, 0.5);
+    double yb = dadd(dmul(0.5, ge ? xm : zb), 0.5);
+    double x2b = __ddiv_rn(zb, yb);
+    double zz = dmul(x2b, x2b);
+    zz = dmul(x2b, __ddiv_rn(dmul(zz, poly2(zz, -6.41409952958715622951e1, 1.63866645699558079767e1, -7.89580278884799154124e-1)),
+                             poly3(zz, -7.69691943550460008604e2, 3.12093766372244180303e2, -3.56722798256324312549e1, 1.00000000000000000000e0)));
+    double r_big = dadd(dfma(-e, 2.121944400546905827679e-4, zz), x2b);
+    /* small exponent: log(1+x) = x - x^2/2 + x^3 P(x)/Q(x) */
+    double x2s = dsub(ge ? xm : dadd(xm, xm), 1.0);
+    double zs = dmul(x2s, x2s);
+    double ys = dmul(x2s, __ddiv_rn(dmul(zs, poly5(x2s, 7.70838733755885391666e0, 1.79368678507819816313e1, 1.44989225341610930846e1,
+                                                     4.70579119878881725854e0, 4.97494994976747001425e-1, 1.01875663804580931796e-4)),
+                                   poly5(x2s, 2.31251620126765340583e1, 7.11544750618563894466e1, 8.29875266912776603211e1,
+                                         4.52279145837532221105e1, 1.12873587189167450590e1, 1.00000000000000000000e0)));
+    ys = dfma(-e, 2.121944400546905827679e-4, ys);
+    double r_small = dadd(x2s, dfma(-0.5, zs, ys));
+    double r = e_big ? r_big : r_small;
+    r = dfma(e, 0.693359375, r);
+    if (x == dbits(0x7ff0000000000000ull)) r = dbits(0x7ff0000000000000ull);
+    if (x == 0.0) r = dbits(0xfff0000000000000ull);
+    return valid ? r : dbits(~0ull);
+}
+
 /* safe_mul / safe_fmadd: src/autodiff/autodiff.cpp:1191-1221 */
 __device__ __forceinline__ float mul_nz(float a, float b) {
     return (a == 0.f || b == 0.f) ? 0.f : fmul(a, b);

@@ -146,6 +146,20 @@ int ref_fmadd_f32(const float *a_, const float *b_, const float *c_, float *out,
     return 0;
 }
 
+int ref_unary_f64(const char *name, const double *in, double *out, size_t n) {
+    using DoubleX = DynamicArray<Packet<double, 4>>;
+    DoubleX x = DoubleX::copy(in, n), r;
+    std::string s(name);
+    if      (s == "sin")  r = sin(x);
+    else if (s == "cos")  r = cos(x);
+    else if (s == "exp")  r = exp(x);
+    else if (s == "log")  r = log(x);
+    else if (s == "sqrt") r = sqrt(x);
+    else return -1;
+    memcpy(out, r.data(), n * sizeof(double));
+    return 0;
+}
+
 /* float -> int32 conversions used by index math */
 void ref_f2i(const float *in, int32_t *out, size_t n) {
     FloatX x = copy_f(in, n);

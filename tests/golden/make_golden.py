@@ -48,6 +48,16 @@ def main():
         d[name] = unary(name, x)
     np.savez_compressed(os.path.join(HERE, "unary.npz"), **d)
 
+    # --- double-precision branches of sin/cos/exp/log
+    x = np.concatenate([np.array([0, -0.0, np.inf, -np.inf, np.nan, 1, -1, 1e-310, 709.5, -709.5, 710, -710, 8191.5, -8191.5]),
+                        rng.uniform(-700, 700, 1000), np.exp(rng.uniform(-700, 700, 1000))]).astype(np.float64)
+    d = {"x": x}
+    for name in ("sin", "cos", "exp", "log", "sqrt"):
+        out = np.zeros_like(x)
+        assert R.ref_unary_f64(name.encode(), P(x), P(out), SZ(len(x))) == 0
+        d[name] = out
+    np.savez_compressed(os.path.join(HERE, "unary_f64.npz"), **d)
+
     # --- C3 histogram: PCG32 samples -> erfinv -> 31 bins (tests/histogram.cpp:41-57), 2^16 samples
     n = 1 << 16
     u = np.zeros(n, np.float32)

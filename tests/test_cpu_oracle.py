@@ -36,6 +36,17 @@ def test_unary_golden(oracle, P, name, which):
     assert same.all(), (name, x[~same][:5], out[~same][:5], want[~same][:5])
 
 
+@pytest.mark.parametrize("name,which", [("sin", 0), ("cos", 1), ("exp", 2), ("log", 3), ("sqrt", 4)])
+def test_unary_f64_golden(oracle, P, name, which):
+    """Double branches of array_math.h sincos/exp/log against vectors from the unmodified reference."""
+    g = np.load(os.path.join(GOLD, "unary_f64.npz"))
+    x = g["x"]; out = np.zeros_like(x)
+    oracle.or_unary_f64(which, P(x), P(out), SZ(len(x)))
+    want = g[name]
+    same = (out.view(np.uint64) == want.view(np.uint64)) | (np.isnan(out) & np.isnan(want))
+    assert same.all(), (name, x[~same][:5], out[~same][:5], want[~same][:5])
+
+
 def test_transcendental_ulp_bounds(oracle, P, ulp):
     """The reference's own accuracy pins: tests/explog.cpp:65-88 (exp <= 3 ulp on [-20,30], log <= 2 ulp)
     and tests/trig.cpp:3-22 (sin <= 19, cos <= 47 ulp on [-8192, 8192]) against libm in double."""

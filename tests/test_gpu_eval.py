@@ -111,6 +111,27 @@ def test_unary_f32(gpu, oracle, ref, P, ulp, name, which, lo, hi, tol):
         assert ulp(got, exact).max() <= 1
 
 
+@pytest.mark.parametrize("name,which", [("sin", 0), ("cos", 1), ("exp", 2), ("log", 3), ("sqrt", 4)])
+def test_unary_f64(gpu, oracle, P, name, which):
+    """Float64 arrays follow the reference's double Cephes branches (array_math.h:261-367, 711-898);
+    arithmetic is IEEE double, so the bar is bit-exact against the oracle, plus the golden vectors."""
+    ek = gpu
+    n = 1 << 16
+    rng = np.random.default_rng(40 + which)
+    x = {"sin": lambda: rng.uniform(-8192, 8192, n), "cos": lambda: rng.uniform(-8192, 8192, n),
+         "exp": lambda: rng.uniform(-720, 720, n), "log": lambda: np.exp(rng.uniform(-700, 700, n)),
+         "sqrt": lambda: rng.uniform(0, 1e20, n)}[name]().astype(np.float64)
+    x[:8] = [0, -0.0, np.inf, -np.inf, np.nan, 1, -1, 1e-310]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unary_f64.npz"))
+    for xs, want in ((x, None), (g["x"], g[name])):
+        got = getattr(ek, name)(ek.Float64.copy(xs)).numpy()
+        if want is None:
+            want = np.zeros(len(xs), np.float64)
+            oracle.or_unary_f64(which, P(xs), P(want), SZ(len(xs)))
+        same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (name, xs[~same][:4], got[~same][:4], want[~same][:4])
+
+
 def test_transcendental_accuracy_vs_libm(gpu, ulp):
     """tests/explog.cpp:65-88 and tests/trig.cpp:3-22 bounds against libm in double."""
     ek = gpu
