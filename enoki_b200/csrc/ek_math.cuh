@@ -118,6 +118,85 @@ __device__ __forceinline__ float log_f32(float x) {
     return valid ? r : fbits(0xffffffffu);
 }
 
+/* ---------------- packed single precision (Blackwell FFMA2) ----------------
+   sm_100 executes two independent IEEE fp32 fused multiply-adds per instruction (PTX fma.rn.f32x2, SASS FFMA2).
+   The interpreter is bound by instruction issue, not by the fp32 pipe, so the polynomial bodies below process
+   two elements per instruction.  Every packed operation is an FMA with exact identities, so each half is
+   rounded exactly like the scalar code above:
+       a * b  = fma(a, b, -0)        (the sum with -0 is exact, also for +-0 products)
+       a + b  = fma(a, 1, b)         a - b = fma(b, -1, a)
+   (mul.rn.f32x2 followed by add.rn.f32x2 is NOT used: ptxas 12.9 contracts that pair into one FFMA2 --
+   tools/micro/f32x2.cu -- which would change the rounding.) */
+struct f2 { float x, y; };
+__device__ __forceinline__ f2 mk2(float v) { return f2{ v, v }; }
+__device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("{\n .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
+        " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd;\n}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return ffma2(a, b, mk2(-0.f)); }
+__device__ __forceinline__ f2 fadd2(f2 a, f2 b) { return ffma2(a, mk2(1.f), b); }
+__device__ __forceinline__ f2 fsub2(f2 a, f2 b) { return ffma2(b, mk2(-1.f), a); }
+__device__ __forceinline__ f2 ffma2(f2 a, float b, float c) { return ffma2(a, mk2(b), mk2(c)); }
+__device__ __forceinline__ f2 ffma2(f2 a, float b, f2 c) { return ffma2(a, mk2(b), c); }
+__device__ __forceinline__ f2 fmul2(f2 a, float b) { return fmul2(a, mk2(b)); }
+
+__device__ __forceinline__ f2 poly2(f2 x, float c0, float c1, float c2) {
+    f2 x2 = fmul2(x, x);
+    return ffma2(x2, c2, ffma2(x, c1, c0));
+}
+__device__ __forceinline__ f2 poly5(f2 x, float c0, float c1, float c2, float c3, float c4, float c5) {
+    f2 x2 = fmul2(x, x), x4 = fmul2(x2, x2);
+    return ffma2(x2, ffma2(x, c3, c2), ffma2(x4, ffma2(x, c5, c4), ffma2(x, c1, c0)));
+}
+/* two elements of sincos_approx (same steps as sincos<> above) */
+template <bool Sin, bool Cos>
+__device__ __forceinline__ void sincos2(f2 x, f2 &s_out, f2 &c_out) {
+    f2 xa = { fabsf(x.x), fabsf(x.y) };
+    f2 q = fmul2(xa, 1.2732395447351626862f);
+    int32_t j0 = (cvtt_sat(q.x) + 1) & ~1, j1 = (cvtt_sat(q.y) + 1) & ~1;
+    f2 y = { __int2float_rn(j0), __int2float_rn(j1) };
+    y = fsub2(fsub2(fsub2(xa, fmul2(y, 0.78515625f)), fmul2(y, 2.4187564849853515625e-4f)),
+              fmul2(y, 3.77489497744594108e-8f));
+    f2 z = fmul2(y, y);
+    if (xa.x == __int_as_float(0x7f800000)) z.x = fbits(0xffffffffu);
+    if (xa.y == __int_as_float(0x7f800000)) z.y = fbits(0xffffffffu);
+    f2 s = fmul2(poly2(z, -1.6666654611e-1f, 8.3321608736e-3f, -1.9515295891e-4f), z);
+    f2 c = fmul2(poly2(z, 4.166664568298827e-2f, -1.388731625493765e-3f, 2.443315711809948e-5f), z);
+    s = ffma2(s, y, y);
+    c = ffma2(c, z, ffma2(z, -0.5f, 1.f));
+    bool p0 = (j0 & 2) == 0, p1 = (j1 & 2) == 0;
+    if (Sin) {
+        s_out.x = fbits(ubits(p0 ? s.x : c.x) ^ ((((uint32_t) j0 << 29) ^ ubits(x.x)) & 0x80000000u));
+        s_out.y = fbits(ubits(p1 ? s.y : c.y) ^ ((((uint32_t) j1 << 29) ^ ubits(x.y)) & 0x80000000u));
+    }
+    if (Cos) {
+        c_out.x = fbits(ubits(p0 ? c.x : s.x) ^ (((uint32_t) (~(j0 - 2)) << 29) & 0x80000000u));
+        c_out.y = fbits(ubits(p1 ? c.y : s.y) ^ (((uint32_t) (~(j1 - 2)) << 29) & 0x80000000u));
+    }
+}
+__device__ __forceinline__ f2 sin_f32x2(f2 x) { f2 s, c; sincos2<true, false>(x, s, c); return s; }
+__device__ __forceinline__ f2 cos_f32x2(f2 x) { f2 s, c; sincos2<false, true>(x, s, c); return c; }
+/* two elements of exp_f32 */
+__device__ __forceinline__ f2 exp_f32x2(f2 x) {
+    const float max_range = +88.3762588501f, min_range = -88.3762588501f;
+    f2 t = ffma2(x, 1.4426950408889634073599f, 0.5f);
+    f2 n = { floorf(t.x), floorf(t.y) };
+    f2 nn = { -n.x, -n.y };
+    f2 xr = ffma2(nn, 0.693359375f, x);
+    xr = ffma2(nn, -2.12194440e-4f, xr);
+    f2 z = poly5(xr, 5.0000001201e-1f, 1.6666665459e-1f, 4.1665795894e-2f,
+                     8.3334519073e-3f, 1.3981999507e-3f, 1.9875691500e-4f);
+    z = ffma2(z, fmul2(xr, xr), fadd2(xr, mk2(1.f)));
+    f2 sc = { fbits((uint32_t) (cvtt_sat(n.x) + 0x7f) << 23), fbits((uint32_t) (cvtt_sat(n.y) + 0x7f) << 23) };
+    f2 r = fmul2(z, sc);
+    r.x = x.x > max_range ? __int_as_float(0x7f800000) : (x.x < min_range ? 0.f : r.x);
+    r.y = x.y > max_range ? __int_as_float(0x7f800000) : (x.y < min_range ? 0.f : r.y);
+    return r;
+}
+
 /* ---------------- double precision (array_math.h, the `!Single` branches) ---------------- */
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }

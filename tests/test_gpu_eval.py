@@ -8,6 +8,7 @@ path is rcpps/rsqrtps + 1 Newton step and is itself CPU-vendor dependent);
 float scatter_add totals <= 1e-5 relative (atomic order).
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
