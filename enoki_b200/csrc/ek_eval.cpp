@@ -1385,7 +1385,8 @@ static int eval_impl(bool dry, std::string *dump) {
             for (const EkInstr &in : a.body) *dstp++ = in;
             for (const EkInstr &in : a.fini) *dstp++ = in;
         }
-        ek_cuda_check(ek_launch_sweep(cfg.V, inline_prog, args, grid, cfg.T, cfg.smem, ctx.stream));
+        const bool core32 = !a.has64 && !a.noncore && inline_prog;     /* 32-bit-only program: kernels without high planes */
+        ek_cuda_check(ek_launch_sweep(cfg.V, inline_prog, core32, args, grid, cfg.T, cfg.smem, ctx.stream));
         if (ctx.timing) {
             ek_cuda_check(cudaEventRecord(ctx.ev_stop, ctx.stream));
             ek_cuda_check(cudaEventSynchronize(ctx.ev_stop));

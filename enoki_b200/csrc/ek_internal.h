@@ -91,7 +91,7 @@ void ek_cuda_check_impl(cudaError_t err, const char *file, int line);
 #define ek_cuda_check(x) ek_cuda_check_impl((x), __FILE__, __LINE__)
 
 /* kernels (defined in .cu files) */
-cudaError_t ek_launch_sweep(int V, bool inline_prog, const EkSweepArgs &args, unsigned grid, unsigned block,
+cudaError_t ek_launch_sweep(int V, bool inline_prog, bool core32, const EkSweepArgs &args, unsigned grid, unsigned block,
                             size_t smem_bytes, cudaStream_t stream);
 void ek_launch_fill(void *ptr, size_t elem_size, uint64_t value, size_t n, cudaStream_t stream);
 void ek_launch_reverse(void *out, const void *in, size_t elem_size, size_t n, cudaStream_t stream);
