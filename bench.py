@@ -477,8 +477,10 @@ def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
     steps = 5
     L.ek_stats_reset()
     L.ek_timer_start()
+    t_host0 = time.perf_counter()
     for _ in range(steps):
         run(False)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / steps     # host time to describe + enqueue one backward()
     ms = L.ek_timer_stop()
     st = ek.stats()
     if dist is not None:
@@ -501,7 +503,7 @@ def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
                         "frac": bytes_alg / (ms_per * 1e-3) / 1e9 / peak_gbs, "bytes_per_edge_adjoint": 10.0,
                         "weights_only_frac": 4.0 * edge_adjoints / (ms_per * 1e-3) / 1e9 / peak_gbs,
                         "note": "whole backward() incl. host scheduling and 80 per-level launches"},
-           "launches_per_backward": int(st.adjoint_launches) // steps, "adjoint_kernels_ms_sum": kern_ms,
+           "launches_per_backward": int(st.adjoint_launches) // steps, "host_enqueue_ms": host_ms, "adjoint_kernels_ms_sum": kern_ms,
            "adjoint_kernels_frac": bytes_alg / (kern_ms * 1e-3) / 1e9 / peak_gbs}
     # final pass frees the graph; leaf gradients stay readable
     run(True)

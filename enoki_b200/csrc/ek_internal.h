@@ -61,6 +61,10 @@ struct EkContext {
     std::unordered_map<const void *, uint32_t> ptr_map;    /* jit.cu:178-179 */
     uint32_t scatter_gather_operand = 0;
     std::vector<std::pair<void (*)(void *), void *>> callbacks;
+    /* work that was recorded but not launched yet (batched adjoint levels): must reach the stream before the
+       allocator synchronises and trims, because that work may still read blocks on the free list */
+    void (*pre_trim_hook)(void *) = nullptr;
+    void *pre_trim_arg = nullptr;
 
     /* allocator (jit.cu:1636-1896): exact-size free lists, stream ordered */
     std::unordered_map<void *, size_t> alloc_size;          /* device + managed */

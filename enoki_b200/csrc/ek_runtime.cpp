@@ -149,6 +149,7 @@ static void *alloc_impl(int kind, size_t size) {
         cudaError_t err = do_alloc();
         if (err == cudaErrorMemoryAllocation) {       /* jit.cu:1715-1723: sync, trim, retry once */
             cudaGetLastError();
+            if (ctx.pre_trim_hook) ctx.pre_trim_hook(ctx.pre_trim_arg);
             ek_sync(); ek_malloc_trim();
             err = do_alloc();
         }

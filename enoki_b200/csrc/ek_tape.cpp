@@ -51,6 +51,25 @@ struct TNode {
     uint32_t size = 0;
 };
 
+/* set of node ids with O(1) insert / membership; iteration is in ascending id order (what std::set gave the
+   reference, autodiff.cpp:157) but sorted only once, when the sweep starts */
+struct IdSet {
+    std::vector<uint32_t> items;
+    std::vector<uint8_t> mark;
+    bool sorted = true;
+    bool count(uint32_t k) const { return k < mark.size() && mark[k]; }
+    void insert(uint32_t k) {
+        if (k >= mark.size()) mark.resize((size_t) k + 1 + mark.size() / 2, 0);
+        if (mark[k]) return;
+        mark[k] = 1;
+        if (!items.empty() && k < items.back()) sorted = false;
+        items.push_back(k);
+    }
+    void clear() { for (uint32_t k : items) mark[k] = 0; items.clear(); sorted = true; }
+    bool empty() const { return items.empty(); }
+    const std::vector<uint32_t> &ordered() { if (!sorted) { std::sort(items.begin(), items.end()); sorted = true; } return items; }
+};
+
 struct Tape {
     ek_type vt = EK_FLOAT32;
     std::unordered_map<uint32_t, TNode> nodes;
@@ -61,7 +80,7 @@ struct Tape {
     bool sg_permute = false;
     uint32_t log_level = 0;
     bool graph_simplification = true, is_simplified = true;
-    std::set<uint32_t> scheduled;
+    IdSet scheduled;
     /* staging for adjoint descriptors (persistent, grown on demand) */
     void *h_stage = nullptr, *d_stage = nullptr;
     size_t stage_bytes = 0;
@@ -349,7 +368,7 @@ void finalize_target(Tape &T, uint32_t tidx, bool free_graph) {
 
 int backward_impl(Tape &T, bool free_graph) {
     EkContext &ctx = ek_ctx();
-    std::vector<uint32_t> sched(T.scheduled.begin(), T.scheduled.end());     /* ascending */
+    std::vector<uint32_t> sched(T.scheduled.ordered());     /* ascending */
     if (sched.empty()) return 0;
     if (ek_init() != 0) return -1;
     if (free_graph) for (uint32_t idx : sched) inc_ref_ext(T, idx);
@@ -363,8 +382,9 @@ int backward_impl(Tape &T, bool free_graph) {
         TNode *n = nullptr;
         uint32_t level = 0, remaining = 0;
         int32_t block = -1;                                  /* level block that holds this node's adjoint */
-        std::vector<std::pair<uint32_t, TEdge *>> out;      /* (target position, edge) */
     };
+    typedef std::pair<uint32_t, TEdge *> OutEdge;            /* (target position, edge) */
+    struct OutRange { OutEdge *b, *e; OutEdge *begin() const { return b; } OutEdge *end() const { return e; } size_t size() const { return (size_t) (e - b); } };
     /* adjoints of interior nodes of one level share ONE allocation (views into it); the block goes back
        to the allocator when the last of them has been consumed.  Leaves keep individual buffers: their
        gradients outlive backward(). */
@@ -376,17 +396,26 @@ int backward_impl(Tape &T, bool free_graph) {
     uint32_t max_level = 0;
     bool need_eval = false;
     size_t total_terms = 0;
+    /* out-edge lists in CSR form (no per-node allocations): count, prefix-sum, fill */
+    std::vector<uint32_t> out_start(S + 1, 0);
+    auto src_pos = [&](const TEdge &e) -> uint32_t {
+        if (e.source < id_base || e.source - id_base >= pos_of.size()) return UINT32_MAX;
+        return pos_of[e.source - id_base];
+    };
+    for (size_t i = 0; i < S; ++i)
+        for (TEdge &e : sn[i].n->edges) { uint32_t p = src_pos(e); if (p != UINT32_MAX) { ++out_start[p + 1]; ++total_terms; } }
+    for (size_t i = 0; i < S; ++i) out_start[i + 1] += out_start[i];
+    std::vector<OutEdge> out_items(total_terms);
+    std::vector<uint32_t> cursor(out_start.begin(), out_start.end() - 1);
     for (size_t i = S; i-- > 0;) {
         TNode &t = *sn[i].n;
         sn[i].remaining = (uint32_t) t.edges.size();
         for (TEdge &e : t.edges) {
-            if (e.source < id_base || e.source - id_base >= pos_of.size()) continue;
-            uint32_t p = pos_of[e.source - id_base];
+            uint32_t p = src_pos(e);
             if (p == UINT32_MAX) continue;
             sn[p].level = std::max(sn[p].level, sn[i].level + 1);
             max_level = std::max(max_level, sn[p].level);
-            sn[p].out.emplace_back((uint32_t) i, &e);
-            ++total_terms;
+            out_items[cursor[p]++] = OutEdge((uint32_t) i, &e);
             if (!e.special) {
                 const EkVariable &w = ctx.vars[e.weight];
                 uint64_t bits;
@@ -394,6 +423,7 @@ int backward_impl(Tape &T, bool free_graph) {
             }
         }
     }
+    auto out_of = [&](uint32_t p) -> OutRange { return OutRange{ out_items.data() + out_start[p], out_items.data() + out_start[p + 1] }; };
     if (need_eval && ek_eval() != 0) return -1;           /* materialise all edge weights at once */
 
     std::vector<std::vector<uint32_t>> by_level(max_level + 1);
@@ -432,12 +462,48 @@ int backward_impl(Tape &T, bool free_graph) {
     for (uint32_t p : by_level[0])
         if (sn[p].n->edges.empty()) finalize(p);
 
+    /* Level launches are batched: the host builds the descriptors of consecutive levels back to back in the pinned
+       staging area and flush() sends them with ONE copy followed by the launches, so the stream sees kernel after
+       kernel instead of copy / kernel / copy ... (a few levels per batch, so that the GPU already works on the first
+       levels while the host describes the next ones).  Anything that enqueues other work (generic path, ek_eval, an
+       allocator trim) flushes first; the levels still execute in order. */
+    struct PendingLaunch { size_t o_jobs, o_terms, o_chunks, end; uint32_t n_jobs, n_chunks; };
+    struct Batch {
+        std::vector<PendingLaunch> items;
+        Tape *T; EkContext *ctx; uint8_t *hst, *dst_dev;
+        void flush() {
+            if (items.empty()) return;
+            ek_cuda_check(cudaMemcpyAsync(dst_dev + items.front().o_jobs, hst + items.front().o_jobs,
+                                          items.back().end - items.front().o_jobs, cudaMemcpyHostToDevice, ctx->stream));
+            for (const PendingLaunch &pl : items) {
+                unsigned grid = std::min<uint32_t>(pl.n_chunks, (uint32_t) ctx->num_sms * 8u);
+                if (ctx->timing) ek_cuda_check(cudaEventRecord(ctx->ev_start, ctx->stream));
+                ek_cuda_check(ek_launch_adjoint(T->vt == EK_FLOAT64, (const EkAdjJob *) (dst_dev + pl.o_jobs), (const EkAdjTerm *) (dst_dev + pl.o_terms),
+                                                (const uint32_t *) (dst_dev + pl.o_chunks), pl.n_jobs, pl.n_chunks, grid, ctx->stream));
+                if (ctx->timing) {
+                    ek_cuda_check(cudaEventRecord(ctx->ev_stop, ctx->stream));
+                    ek_cuda_check(cudaEventSynchronize(ctx->ev_stop));
+                    float ms = 0; ek_cuda_check(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+                    ctx->stats.last_kernel_ms = ms; ctx->stats.total_kernel_ms += ms;
+                }
+                ctx->stats.launches++; ctx->stats.adjoint_launches++;
+            }
+            items.clear();
+        }
+    } batch;
+    batch.T = &T; batch.ctx = &ctx; batch.hst = hst; batch.dst_dev = dst_dev;
+    struct HookGuard {
+        EkContext &c;
+        HookGuard(EkContext &c_, Batch *b) : c(c_) { c.pre_trim_hook = [](void *p) { ((Batch *) p)->flush(); }; c.pre_trim_arg = b; }
+        ~HookGuard() { c.pre_trim_hook = nullptr; c.pre_trim_arg = nullptr; }
+    } hook_guard(ctx, &batch);
+
     for (uint32_t L = 1; L <= max_level; ++L) {
         done.clear(); generic.clear();
         /* descriptors are written straight into the pinned staging area */
         const size_t n_src = by_level[L].size();
         size_t n_terms_lvl = 0;
-        for (uint32_t p : by_level[L]) n_terms_lvl += sn[p].out.size();
+        for (uint32_t p : by_level[L]) n_terms_lvl += out_of(p).size();
         size_t o_jobs = stage_off, o_terms = (o_jobs + n_src * sizeof(EkAdjJob) + 15) & ~(size_t) 15;
         size_t o_chunks = (o_terms + n_terms_lvl * sizeof(EkAdjTerm) + 15) & ~(size_t) 15;
         size_t end_max = (o_chunks + n_src * 4 + 15) & ~(size_t) 15;
@@ -456,7 +522,7 @@ int backward_impl(Tape &T, bool free_graph) {
             TNode &s = *S_.n;
             /* classify */
             bool simple = s.grad == 0;
-            for (auto &te : S_.out) {
+            for (auto &te : out_of(p)) {
                 if (!simple) break;
                 TNode &t = *sn[te.first].n;
                 if (te.second->special) { simple = false; break; }
@@ -470,6 +536,7 @@ int backward_impl(Tape &T, bool free_graph) {
                     if ((gv.data == nullptr && !var_imm(t.grad, bits)) || gv.dirty) {
                         /* adjoint produced by the generic path: still an unevaluated trace, or a buffer with
                            pending scatter_add side effects (gather edges) */
+                        batch.flush();
                         if (ek_eval() != 0) return -1;
                     }
                 }
@@ -478,7 +545,7 @@ int backward_impl(Tape &T, bool free_graph) {
 
             EkAdjJob job;
             job.first_term = n_terms; job.n_terms = 0; job.size = s.size; job.aligned = 1;
-            for (auto &te : S_.out) {
+            for (auto &te : out_of(p)) {
                 TNode &t = *sn[te.first].n;
                 if (!t.grad) continue;                      /* empty adjoint contributes nothing */
                 EkAdjTerm &term = terms[n_terms]; term.pad = 0;
@@ -517,42 +584,33 @@ int backward_impl(Tape &T, bool free_graph) {
 
         if (n_jobs) {
             size_t end = (o_chunks + (size_t) n_jobs * 4 + 15) & ~(size_t) 15;
-            ek_cuda_check(cudaMemcpyAsync(dst_dev + o_jobs, hst + o_jobs, end - o_jobs, cudaMemcpyHostToDevice, ctx.stream));
-            unsigned grid = std::min<uint32_t>(n_chunks, (uint32_t) ctx.num_sms * 8u);
-            if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
-            ek_cuda_check(ek_launch_adjoint(T.vt == EK_FLOAT64, (const EkAdjJob *) (dst_dev + o_jobs), (const EkAdjTerm *) (dst_dev + o_terms),
-                                            (const uint32_t *) (dst_dev + o_chunks), n_jobs, n_chunks, grid, ctx.stream));
-            if (ctx.timing) {
-                ek_cuda_check(cudaEventRecord(ctx.ev_stop, ctx.stream));
-                ek_cuda_check(cudaEventSynchronize(ctx.ev_stop));
-                float ms = 0; ek_cuda_check(cudaEventElapsedTime(&ms, ctx.ev_start, ctx.ev_stop));
-                ctx.stats.last_kernel_ms = ms; ctx.stats.total_kernel_ms += ms;
-            }
-            ctx.stats.launches++; ctx.stats.adjoint_launches++;
+            batch.items.push_back({ o_jobs, o_terms, o_chunks, end, n_jobs, n_chunks });
             stage_off = end;
         }
+        /* small batches keep the GPU busy while the host prepares the following levels */
+        if (!generic.empty() || ctx.timing || batch.items.size() >= (L <= 2 ? 1u : 6u)) batch.flush();
 
         /* generic sources of this level (special edges, hsum into scalars, pre-seeded grads) */
         for (uint32_t p : generic) {
             std::vector<std::pair<uint32_t, TEdge *>> out;
-            out.reserve(sn[p].out.size());
-            for (auto &te : sn[p].out) out.emplace_back(sched[te.first], te.second);
+            out.reserve(out_of(p).size());
+            for (auto &te : out_of(p)) out.emplace_back(sched[te.first], te.second);
             if (accumulate_generic(T, sched[p], *sn[p].n, out) != 0) return -1;
             done.push_back(p);
         }
 
         /* bookkeeping: every processed source has consumed one in-edge of each of its targets */
         for (uint32_t p : done) {
-            for (auto &te : sn[p].out) {
+            for (auto &te : out_of(p)) {
                 SNode &tn = sn[te.first];
                 if (tn.remaining > 0 && --tn.remaining == 0) finalize(te.first);
             }
-            sn[p].out.clear();
             /* a source without in-edges (leaf) is complete now */
             if (sn[p].remaining == 0 && sn[p].n->edges.empty()) finalize(p);
         }
         if (blocks[L].base && blocks[L].pending == 0 && !any_generic) { ek_free(blocks[L].base); blocks[L].base = nullptr; }
     }
+    batch.flush();
     ek_cuda_check(cudaEventRecord(T.stage_done, ctx.stream));
     /* blocks that could not be released early (the generic path may hold unevaluated traces that read
        adjoint views): evaluate, then release */
@@ -572,7 +630,7 @@ int backward_impl(Tape &T, bool free_graph) {
 
 /* forward mode, autodiff.cpp:912-988 (recorded through the evaluator) */
 int forward_impl(Tape &T, bool free_graph) {
-    std::vector<uint32_t> sched(T.scheduled.begin(), T.scheduled.end());
+    std::vector<uint32_t> sched(T.scheduled.ordered());
     if (free_graph) for (uint32_t idx : sched) inc_ref_ext(T, idx);
     for (uint32_t sidx : sched) {
         auto sit = T.nodes.find(sidx);
