@@ -63,6 +63,8 @@ struct EkContext {
     std::vector<std::pair<void (*)(void *), void *>> callbacks;
     /* work that was recorded but not launched yet (batched adjoint levels): must reach the stream before the
        allocator synchronises and trims, because that work may still read blocks on the free list */
+    cudaStream_t d2h_stream = nullptr;          /* read-back stream of ek_memcpy_from_device_overlapped() */
+    cudaEvent_t d2h_event = nullptr;
     void (*pre_trim_hook)(void *) = nullptr;
     void *pre_trim_arg = nullptr;
 

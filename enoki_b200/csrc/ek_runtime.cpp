@@ -224,9 +224,24 @@ void ek_memcpy_from_device_async(void *dst, const void *src, size_t size) {
     ek_cuda_check(cudaMemcpyAsync(dst, src, size, cudaMemcpyDeviceToHost, ctx.stream));
 }
 
+/* Extension (no reference counterpart): read-back on a second stream, so that it overlaps with host-to-device copies
+   and kernels enqueued afterwards (PCIe is full duplex).  Ordered after everything enqueued so far; `src` must stay
+   allocated until the next ek_sync(). */
+void ek_memcpy_from_device_overlapped(void *dst, const void *src, size_t size) {
+    EkContext &ctx = ek_ctx(); ek_init();
+    if (!ctx.d2h_stream) {
+        ek_cuda_check(cudaStreamCreateWithFlags(&ctx.d2h_stream, cudaStreamNonBlocking));
+        ek_cuda_check(cudaEventCreateWithFlags(&ctx.d2h_event, cudaEventDisableTiming));
+    }
+    ek_cuda_check(cudaEventRecord(ctx.d2h_event, ctx.stream));
+    ek_cuda_check(cudaStreamWaitEvent(ctx.d2h_stream, ctx.d2h_event, 0));
+    ek_cuda_check(cudaMemcpyAsync(dst, src, size, cudaMemcpyDeviceToHost, ctx.d2h_stream));
+}
+
 void ek_sync(void) {
     if (!g_ctx || !g_ctx->initialized) return;
     ek_cuda_check(cudaStreamSynchronize(g_ctx->stream));
+    if (g_ctx->d2h_stream) ek_cuda_check(cudaStreamSynchronize(g_ctx->d2h_stream));
 }
 
 void ek_fill(void *ptr, size_t elem_size, uint64_t value, size_t n) {

@@ -188,6 +188,9 @@ EK_API void  ek_memcpy_to_device(void *dst, const void *src, size_t size);      
 EK_API void  ek_memcpy_to_device_async(void *dst, const void *src, size_t size);
 EK_API void  ek_memcpy_from_device(void *dst, const void *src, size_t size);       /* cuda.h:147 */
 EK_API void  ek_memcpy_from_device_async(void *dst, const void *src, size_t size);
+/* extension: device-to-host copy on the runtime's read-back stream (overlaps with later host-to-device copies and
+   kernels; ordered after all work enqueued so far; keep `src` allocated until ek_sync()) */
+EK_API void  ek_memcpy_from_device_overlapped(void *dst, const void *src, size_t size);
 
 /* ------------------------------------------------------------------ reverse-mode tape
  * One tape per value type (Float32 / Float64) like the reference's static

@@ -105,7 +105,12 @@ int main(int argc, char **argv) {
         printf("  grad[%d] cpu % .8g  gpu % .8g\n", k, gc[k], gg[k]);
         /* the six gradients are sums of n terms with cancellation (d/d delta_z is analytically 0): compare against
            the largest gradient magnitude (float reductions are reassociated, SURVEY 7 hard part 4) */
-        if (std::fabs(gc[k] - gg[k]) > 2e-5 * gmax) fail = 1;
+        /* the CPU reference adds the n per-pixel terms one packet after another: its own rounding error grows
+           with n, so the bound does too */
+        if (std::fabs(gc[k] - gg[k]) > std::max(2e-5, 1e-11 * (double) n) * gmax) fail = 1;
+        /* orthographic rays along z: the image does not depend on delta_z, so that gradient is analytically 0 -- an
+           n-independent check of the device reduction (the CPU value drifts to 4e-5 at 4096^2) */
+        if (k == 2 && std::fabs(gg[k]) > 1e-6 * gmax) fail = 1;
     }
     printf("  time: cpu %.1f ms, gpu first %.1f ms, gpu second %.1f ms\n",
            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),

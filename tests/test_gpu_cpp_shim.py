@@ -20,12 +20,14 @@ def test_cpp_header_shim(gpu):
     assert "all checks passed" in r.stdout
 
 
-def test_cpp_sphere_c5(gpu):
-    """differentiable ray-sphere render, forward + backward, CPU reference tape vs this backend."""
+@pytest.mark.parametrize("res", ["512", "1024", "4096"])
+def test_cpp_sphere_c5(gpu, res):
+    """differentiable ray-sphere render, forward + backward, CPU reference tape vs this backend
+    (4096 = the full 4096 x 4096-ray configuration of BASELINE.json: image compared pixel by pixel)."""
     binp = os.path.join(os.path.dirname(BIN), "sphere_check")
     if not os.path.exists(binp):
         pytest.skip("tests/cpp/sphere_check not built (needs the reference headers at build time)")
-    r = subprocess.run([binp, "512"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([binp, res], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
 
