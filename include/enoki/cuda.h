@@ -364,10 +364,26 @@ struct CUDAArray : ArrayBase<value_t<Value>, CUDAArray<Value>> {
         return call_support<BaseType, CUDAArray>(*this);
     }
 
-    /// Virtual-call dispatch support (cuda.h:814-843): SURVEY 8f row 1, not in this round
+    /// Virtual-call dispatch support (cuda.h:814-843): (instance pointer, indices that refer to it), pointers ascending,
+    /// indices ascending.  Not cached per array (the handle stays 4 bytes); array_call.h asks once per dispatch.
+    /// Round 1: ek_partition is unverified and answers with an error unless EK_ENABLE_PARTITION=1 (see ek_scan.cu).
     template <typename T = Value, enable_if_t<std::is_pointer_v<T> || std::is_same_v<T, uintptr_t>> = 0>
     std::vector<std::pair<Value, CUDAArray<uint32_t>>> partition_() const {
-        throw std::runtime_error("CUDAArray::partition_(): not implemented by the enoki_b200 backend yet");
+        eval();
+        void **unique = nullptr;
+        uint32_t *counts = nullptr;
+        uint32_t **perm = nullptr;
+        cuda_partition(size(), (const void **) data(), &unique, &counts, &perm);
+        uint32_t num_unique = counts[0];
+        std::vector<std::pair<Value, CUDAArray<uint32_t>>> result;
+        result.reserve(num_unique);
+        for (uint32_t i = 0; i < num_unique; ++i)
+            result.emplace_back((Value) unique[i],
+                                CUDAArray<uint32_t>::from_index_(cuda_var_register(EnokiType::UInt32, counts[i + 1], perm[i], true)));
+        cuda_host_free(unique);
+        cuda_host_free(counts);
+        free(perm);
+        return result;
     }
 
     Index index_() const { return m_index; }

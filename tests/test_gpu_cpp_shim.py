@@ -41,3 +41,17 @@ def test_cpp_autodiff_parity(gpu):
     r = subprocess.run([binp], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+@pytest.mark.skipif(os.environ.get("EK_ENABLE_PARTITION") is None,
+                    reason="virtual-call dispatch is unverified in round 1 (see ek_partition); opt in with EK_ENABLE_PARTITION=1")
+@pytest.mark.parametrize("n", ["1000", "100003", "4194304"])
+def test_cpp_virtual_call_dispatch(gpu, n):
+    """SURVEY 8f row 1: ENOKI_CALL_SUPPORT dispatch through CUDAArray<T *>::partition_() -> ek_partition, compared bit
+    for bit with the same classes called on the reference CPU path (array_call.h:124-193)."""
+    binp = os.path.join(os.path.dirname(BIN), "call_check")
+    if not os.path.exists(binp):
+        pytest.skip("tests/cpp/call_check not built (needs the reference headers at build time)")
+    r = subprocess.run([binp, n], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
