@@ -315,7 +315,11 @@ def main():
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     achieved = C2_BYTES_PER_ELEM * n / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "kernel": "ek_sweep_kernel<8>", "kernel_ms": kern_ms,
+                # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
+                # (profiles/r1_v8a_sweep_ncu_summary.txt: dram__bytes_read.sum 1.074 GB + dram__bytes_write.sum 0.249 GB)
+                "traffic": 1.323e9 if n == (1 << 26) else None, "traffic_unit": "B/launch",
+                "algorithmic_bytes": C2_BYTES_PER_ELEM * n,
+                "kernel": "ek_sweep_kernel<16,false,true>", "kernel_ms": kern_ms,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"}
 
     # ---- e2e: pinned host buffers, H2D of the 4 inputs + D2H of the result inside the timed region
