@@ -52,23 +52,49 @@ class ClockSampler:
     def __init__(self, device):
         self.proc = None
         self.device = device
+        self.lines = []
+        self.t_lines = []
+        self.window = [None, None]
 
     def start(self):
+        """Starts `nvidia-smi -lms 100` and waits (<= 5 s) for its first line, so that samples exist during the
+        timed region and not only after it."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+        first = threading.Event()
+
+        def reader():
+            for line in self.proc.stdout:
+                self.lines.append(line); self.t_lines.append(time.time())
+                first.set()
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+        first.wait(5.0)
+
+    def mark_begin(self): self.window[0] = time.time()
+    def mark_end(self): self.window[1] = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
-            self.proc.kill(); out = ""
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        lines = list(self.lines)
+        n_all = len(lines)
+        if self.window[0] is not None and self.window[1] is not None:
+            inside = [l for l, t in zip(lines, self.t_lines) if self.window[0] <= t <= self.window[1] + 0.1]
+            if inside:
+                lines = inside
+        out = "".join(lines)
         sm, smax, reasons = [], None, set()
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -92,7 +118,7 @@ class ClockSampler:
                 pass
         busy = [v for v in sm if smax and v >= 0.5 * smax] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_whole_run": n_all}
 
 
 # --------------------------------------------------------------------------- reference CPU arm
@@ -203,7 +229,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--elems", type=int, default=N_ELEMS, help="elements per GPU (default: the BASELINE config, 2^26)")
@@ -282,6 +308,7 @@ def main():
     barrier()
     L.ek_stats_reset()
     barrier()
+    sampler.mark_begin()
     L.ek_timer_start()
     t0 = time.time()
     keep = None
@@ -289,6 +316,7 @@ def main():
         keep = step()
     ms = L.ek_timer_stop()
     barrier()
+    sampler.mark_end()
     wall_ms = 1e3 * (time.time() - t0)
     st = ek.stats()
     launches = int(st.launches)

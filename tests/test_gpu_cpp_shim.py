@@ -55,3 +55,15 @@ def test_cpp_virtual_call_dispatch(gpu, n):
     r = subprocess.run([binp, n], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+def test_cpp_integer_morton_parity(gpu):
+    """North star: bit-exact integer / indexing / Morton ops.  tests/cpp/int_check.cpp runs the same templates
+    (arithmetic, shifts, mulhi, div/mod, division by constants, popcnt/lzcnt/tzcnt, Morton 2-D/3-D encode + decode,
+    int<->float conversions; uint32/int32/uint64/int64) on the reference CPU path and on this backend."""
+    binp = os.path.join(os.path.dirname(BIN), "int_check")
+    if not os.path.exists(binp):
+        pytest.skip("tests/cpp/int_check not built (needs the reference headers at build time)")
+    r = subprocess.run([binp, "100003"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
