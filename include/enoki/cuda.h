@@ -124,16 +124,29 @@ struct CUDAArray : ArrayBase<value_t<Value>, CUDAArray<Value>> {
 
     // ---- handle semantics: intrusive external reference count (cuda.h:216-258) ----
     CUDAArray() = default;
-    ~CUDAArray() { ek_dec_ref_ext(m_index); }
+    ~CUDAArray() {
+        ek_dec_ref_ext(m_index);
+        if constexpr (std::is_pointer_v<Value> || std::is_same_v<Value, uintptr_t>) delete m_cached_partition;
+    }
     CUDAArray(const CUDAArray &a) : m_index(a.m_index) { ek_inc_ref_ext(m_index); }
-    CUDAArray(CUDAArray &&a) noexcept : m_index(a.m_index) { a.m_index = 0; }
+    CUDAArray(CUDAArray &&a) noexcept : m_index(a.m_index) {
+        a.m_index = 0;
+        if constexpr (std::is_pointer_v<Value> || std::is_same_v<Value, uintptr_t>) {
+            m_cached_partition = a.m_cached_partition; a.m_cached_partition = nullptr;
+        }
+    }
     CUDAArray &operator=(const CUDAArray &a) {
         ek_inc_ref_ext(a.m_index);
         ek_dec_ref_ext(m_index);
         m_index = a.m_index;
+        if constexpr (std::is_pointer_v<Value> || std::is_same_v<Value, uintptr_t>) { delete m_cached_partition; m_cached_partition = nullptr; }
         return *this;
     }
-    CUDAArray &operator=(CUDAArray &&a) noexcept { std::swap(m_index, a.m_index); return *this; }
+    CUDAArray &operator=(CUDAArray &&a) noexcept {
+        std::swap(m_index, a.m_index);
+        if constexpr (std::is_pointer_v<Value> || std::is_same_v<Value, uintptr_t>) std::swap(m_cached_partition, a.m_cached_partition);
+        return *this;
+    }
 
     /// Converting constructor: float -> int truncates, int -> float rounds to nearest (cuda.h:236-247)
     template <typename T> CUDAArray(const CUDAArray<T> &v)
@@ -365,25 +378,27 @@ struct CUDAArray : ArrayBase<value_t<Value>, CUDAArray<Value>> {
     }
 
     /// Virtual-call dispatch support (cuda.h:814-843): (instance pointer, indices that refer to it), pointers ascending,
-    /// indices ascending.  Not cached per array (the handle stays 4 bytes); array_call.h asks once per dispatch.
+    /// indices ascending; cached per array like the reference's.
     /// Round 1: ek_partition is unverified and answers with an error unless EK_ENABLE_PARTITION=1 (see ek_scan.cu).
     template <typename T = Value, enable_if_t<std::is_pointer_v<T> || std::is_same_v<T, uintptr_t>> = 0>
     std::vector<std::pair<Value, CUDAArray<uint32_t>>> partition_() const {
-        eval();
-        void **unique = nullptr;
-        uint32_t *counts = nullptr;
-        uint32_t **perm = nullptr;
-        cuda_partition(size(), (const void **) data(), &unique, &counts, &perm);
-        uint32_t num_unique = counts[0];
-        std::vector<std::pair<Value, CUDAArray<uint32_t>>> result;
-        result.reserve(num_unique);
-        for (uint32_t i = 0; i < num_unique; ++i)
-            result.emplace_back((Value) unique[i],
-                                CUDAArray<uint32_t>::from_index_(cuda_var_register(EnokiType::UInt32, counts[i + 1], perm[i], true)));
-        cuda_host_free(unique);
-        cuda_host_free(counts);
-        free(perm);
-        return result;
+        if (!m_cached_partition) {
+            eval();
+            void **unique = nullptr;
+            uint32_t *counts = nullptr;
+            uint32_t **perm = nullptr;
+            cuda_partition(size(), (const void **) data(), &unique, &counts, &perm);
+            uint32_t num_unique = counts[0];
+            m_cached_partition = new std::vector<std::pair<Value, CUDAArray<uint32_t>>>();
+            m_cached_partition->reserve(num_unique);
+            for (uint32_t i = 0; i < num_unique; ++i)
+                m_cached_partition->emplace_back((Value) unique[i],
+                    CUDAArray<uint32_t>::from_index_(cuda_var_register(EnokiType::UInt32, counts[i + 1], perm[i], true)));
+            cuda_host_free(unique);
+            cuda_host_free(counts);
+            free(perm);
+        }
+        return *m_cached_partition;
     }
 
     Index index_() const { return m_index; }
@@ -420,8 +435,13 @@ protected:
         cuda_var_mark_side_effect(detail::ek_chk(var));
     }
 
+    /* Same object layout as the reference (cuda.h:951-953): the handle plus the cached partition of pointer arrays.
+       The size is part of the contract -- header templates size their recursion by sizeof(Value), e.g. morton.h:56,
+       77 (`Level = clog2i(sizeof(Value) * 8)`): with a 4-byte object the 64-bit Morton decode loses its last step. */
     Index m_index = 0;
+    mutable std::vector<std::pair<Value, CUDAArray<uint32_t>>> *m_cached_partition = nullptr;
 };
+static_assert(sizeof(CUDAArray<float>) == 16, "CUDAArray<T> must keep the reference's 16-byte layout");
 
 template <typename T, enable_if_t<!is_diff_array_v<T> && is_cuda_array_v<T>> = 0>
 ENOKI_INLINE void set_label(const T &a, const char *label) {
