@@ -77,6 +77,7 @@ SIGNATURES = {
     "ek_memcpy_from_device": (None, [c_vp, c_vp, c_sz]),
     "ek_memcpy_from_device_async": (None, [c_vp, c_vp, c_sz]),
     "ek_memcpy_from_device_overlapped": (None, [c_vp, c_vp, c_sz]),
+    "ek_memcpy_device_async": (None, [c_vp, c_vp, c_sz]),
     "ek_tape_append_node": (c_u32, [c_int, c_sz, ctypes.c_char_p]),
     "ek_tape_append_leaf": (c_u32, [c_int, c_sz]),
     "ek_tape_append_edge": (c_int, [c_int, c_u32, c_u32, c_u32]),

@@ -204,6 +204,21 @@ def backward(x, free_graph=True):
         raise _e()
 
 
+def set_gradient(x, value, backward=True):
+    """autodiff.h:1306-1312 / autodiff.cpp:822-836: seeds the gradient of `x` (a Float32 array) and schedules the
+    nodes reachable from it; follow with backward_static() (FloatD.backward() of the reference's Python module)."""
+    from . import Float32, CUDAArray
+    v = value if isinstance(value, CUDAArray) else Float32(value)
+    if _l().ek_tape_set_gradient(EK_FLOAT32, x.index, v.index, int(backward)) != 0:
+        raise _e()
+
+
+def backward_static(free_graph=True):
+    """src/python/cuda_autodiff_1d.cpp:23-35 `FloatD.backward()`"""
+    if _l().ek_tape_backward_static(EK_FLOAT32, int(free_graph)) != 0:
+        raise _e()
+
+
 def forward(x, free_graph=True):
     if _l().ek_tape_forward(EK_FLOAT32, x.index, int(free_graph)) != 0:
         raise _e()

@@ -224,6 +224,12 @@ void ek_memcpy_from_device_async(void *dst, const void *src, size_t size) {
     ek_cuda_check(cudaMemcpyAsync(dst, src, size, cudaMemcpyDeviceToHost, ctx.stream));
 }
 
+/* Extension: device-to-device copy on the runtime's stream (interop with other frameworks' buffers) */
+void ek_memcpy_device_async(void *dst, const void *src, size_t size) {
+    EkContext &ctx = ek_ctx(); ek_init();
+    ek_cuda_check(cudaMemcpyAsync(dst, src, size, cudaMemcpyDeviceToDevice, ctx.stream));
+}
+
 /* Extension (no reference counterpart): read-back on a second stream, so that it overlaps with host-to-device copies
    and kernels enqueued afterwards (PCIe is full duplex).  Ordered after everything enqueued so far; `src` must stay
    allocated until the next ek_sync(). */

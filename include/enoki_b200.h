@@ -191,6 +191,8 @@ EK_API void  ek_memcpy_from_device_async(void *dst, const void *src, size_t size
 /* extension: device-to-host copy on the runtime's read-back stream (overlaps with later host-to-device copies and
    kernels; ordered after all work enqueued so far; keep `src` allocated until ek_sync()) */
 EK_API void  ek_memcpy_from_device_overlapped(void *dst, const void *src, size_t size);
+/* extension: device-to-device copy on the runtime's stream (PyTorch / CuPy interop, src/python/common.h:1085-1215) */
+EK_API void  ek_memcpy_device_async(void *dst, const void *src, size_t size);
 
 /* ------------------------------------------------------------------ reverse-mode tape
  * One tape per value type (Float32 / Float64) like the reference's static
