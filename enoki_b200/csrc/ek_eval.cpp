@@ -675,7 +675,11 @@ struct Assembler {
                 ensure_acc(d1);
                 if (smem_bins) {
                     uint32_t count = (uint32_t) var(v.extra_dep).size;
-                    uint32_t copies = std::max(1u, std::min(32u, 4096u / count));
+                    /* integer bins: up to 32 copies shared by (warp, lane & 3), native shared-memory atomics (ATOMS.ADD).
+                       float bins: a shared-memory float atomicAdd is a compare-and-swap loop (ATOMS.CAST.SPIN) that
+                       crawls under contention, so small float targets get one private copy per thread instead
+                       (plain read-modify-write, bank = thread id, no atomics) */
+                    uint32_t copies = (dop == DOP_SCATTER_ADD_F32 && count <= 32u) ? 256u : std::max(1u, std::min(32u, 4096u / count));
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(copies); out.argw.push_back(pa);
                     out.extra_bytes += (count * copies * 4 + 15) & ~15u;
