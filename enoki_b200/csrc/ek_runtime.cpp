@@ -502,6 +502,29 @@ uint32_t ek_trace_append(ek_type type, ek_op op, uint32_t a, uint32_t b, uint32_
         ek_set_error("ek_trace_append(): scatter target must be a pointer registered with ek_var_register_ptr()");
         return 0;
     }
+    /* x / (+-2^k) == x * (+-2^-k) bit for bit (an exact scaling rounds the same real number), and the multiply is one
+       instruction where div.rn is a Newton iteration with a slow-path branch: rewrite divisions by power-of-two
+       literals (C3's `* 31 / 8`) */
+    if (op == EK_OP_DIV && (type == EK_FLOAT32 || type == EK_FLOAT64)) {
+        const EkVariable &dv = ctx.vars[b];
+        if (dv.op == EK_OP_LITERAL && dv.data == nullptr && dv.size == 1) {
+            uint64_t rbits = 0; bool ok = false;
+            if (type == EK_FLOAT32) {
+                uint32_t bits = (uint32_t) dv.imm, e = (bits >> 23) & 0xffu;
+                if ((bits & 0x7fffffu) == 0 && e >= 2 && e <= 252) { rbits = (bits & 0x80000000u) | ((254u - e) << 23); ok = true; }
+            } else {
+                uint64_t bits = dv.imm, e = (bits >> 52) & 0x7ffull;
+                if ((bits & 0xfffffffffffffull) == 0 && e >= 2 && e <= 2044) { rbits = (bits & 0x8000000000000000ull) | ((2046ull - e) << 52); ok = true; }
+            }
+            if (ok) {
+                uint32_t lit = ek_trace_append(type, EK_OP_LITERAL, 0, 0, 0, rbits);
+                if (!lit) return 0;
+                uint32_t r = ek_trace_append(type, EK_OP_MUL, a, lit, 0, 0);
+                ek_dec_ref_ext(lit);
+                return r;
+            }
+        }
+    }
     bool is_reduce = op >= EK_OP_HSUM && op <= EK_OP_COUNT;
     uint32_t idx = var_new(type);
     EkVariable &v = ctx.vars[idx];

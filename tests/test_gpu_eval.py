@@ -170,6 +170,22 @@ def test_binary_f32_bit_exact(gpu):
     assert ((A * 2.0 + 1.0).numpy() == a * np.float32(2) + np.float32(1)).all()
 
 
+def test_division_by_power_of_two_literal(gpu):
+    """x / (+-2^k) is recorded as a multiplication by the exact reciprocal (ek_trace_append); results must equal a
+    real IEEE division bit for bit, including results that underflow to denormals."""
+    ek = gpu
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.normal(size=5000).astype(np.float32) * np.float32(1e-3),
+                        (rng.integers(0, 1 << 32, 5000, dtype=np.uint64).astype(np.uint32)).view(np.float32),   # every bit pattern class
+                        np.array([0, -0.0, np.inf, -np.inf, np.nan, 1e-38, -1e-38, 1e-45, 3.4e38, 1.17549435e-38], np.float32)])
+    X = ek.Float32.copy(x)
+    with np.errstate(all="ignore"):
+        for d in (8.0, 0.5, -4.0, 1024.0, 2.0 ** -20, 2.0 ** 100, 3.0):
+            got = (X / d).numpy(); want = x / np.float32(d)
+            same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+            assert same.all(), (d, x[~same][:4], got[~same][:4], want[~same][:4])
+
+
 def test_integer_ops_bit_exact(gpu):
     ek = gpu
     rng = np.random.default_rng(6)
