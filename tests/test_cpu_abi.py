@@ -56,6 +56,17 @@ def test_plan_c2_program(ek):
     del out
 
 
+def test_plan_division_by_power_of_two_is_a_multiplication(ek):
+    x = _fake(ek, 1000)
+    a = x / 8.0
+    b = x / 3.0
+    c = x / -0.25
+    plan = ek.debug_plan()
+    body = [l.split()[1] for l in plan.splitlines() if l.strip().startswith("body")]
+    assert body.count("DIV_F32") == 1 and body.count("MUL_F32") == 2, plan
+    del a, b, c
+
+
 def test_plan_reduction_is_epilogue_and_phases(ek):
     n = 4096
     x = _fake(ek, n)
