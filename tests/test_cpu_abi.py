@@ -67,6 +67,31 @@ def test_plan_division_by_power_of_two_is_a_multiplication(ek):
     del a, b, c
 
 
+def test_plan_many_inputs_64bit_and_sizes(ek):
+    n = 100_000
+    # (1) more input streams than staging units: the first 8 are staged (TMA), the rest are direct global loads
+    xs = [ek.Float32.map(0x7f0000000000 + 0x1000000 * k, n) for k in range(12)]
+    acc = xs[0]
+    for x in xs[1:]:
+        acc = acc + x
+    plan = ek.debug_plan()
+    assert "in=8" in plan and plan.count("LDG_32") == 4 and plan.count("ADD_F32") == 11
+    del acc
+    # (2) 64-bit values travel as two planes: unpack of the staged input, 64-bit ops, 64-bit store
+    u = ek.UInt64.map(0x7e0000000000, n)
+    v = (u * ek.UInt64(3)) >> ek.UInt64(5)
+    plan = ek.debug_plan()
+    body = [l.split()[1] for l in plan.splitlines() if l.strip().startswith("body")]
+    assert body == ["LD_64", "MUL_I64", "SHR_U64", "ST_64"] and "tmp_slots=2" in plan
+    del v
+    # (3) one sweep per array size, larger first (jit.cu:1385-1508)
+    a = ek.Float32.map(0x7d0000000000, 1000); b = ek.Float32.map(0x7c0000000000, 5000)
+    r1 = a * 2.0; r2 = b + 1.0
+    sweeps = [l for l in ek.debug_plan().splitlines() if l.startswith("sweep")]
+    assert len(sweeps) == 2 and "n=5000" in sweeps[0] and "n=1000" in sweeps[1]
+    del r1, r2
+
+
 def test_plan_reduction_is_epilogue_and_phases(ek):
     n = 4096
     x = _fake(ek, n)
