@@ -242,7 +242,8 @@ def run_reference(args):
     # K timed "steps": each step = PASSES passes of the whole 2^26-element workload on all host threads, timed by the
     # wall clock around thread start and join (what a caller of the reference would see; the passes amortise the
     # thread start-up).  value and ms_per_step come from the same clock.
-    PASSES = 32
+    t_pass = (c.per * c.threads) / cpu_wall_rate(c, 2)           # seconds per pass, measured (incl. thread start / 2)
+    PASSES = int(max(1, min(32, round(60.0 / (max(args.steps, 1) * t_pass)))))   # whole timed run <= ~1 minute
     t0 = time.time()
     for _ in range(args.steps):
         c.run(PASSES)
