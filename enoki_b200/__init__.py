@@ -370,6 +370,15 @@ def debug_plan():
     return _lib.take_string(p)
 
 
+def debug_program():
+    """The same as JSON with the complete sweep programs (consumed by tests/ek_emulator.py)."""
+    import json
+    p = lib().ek_debug_program()
+    if not p:
+        raise EnokiError(lib().ek_last_error().decode())
+    return json.loads(_lib.take_string(p))
+
+
 def stats():
     s = ek_stats()
     lib().ek_stats_get(ctypes.byref(s))

@@ -114,6 +114,7 @@ SIGNATURES = {
     "ek_flush_l2": (None, []),
     # debugging aid (host-only, not part of the reference-facing ABI)
     "ek_debug_plan": (c_vp, []),
+    "ek_debug_program": (c_vp, []),
 }
 
 _lib = None

@@ -1228,7 +1228,7 @@ void dump_program(std::ostream &os, const Assembled &a, const Group &g) {
 } // namespace
 
 /* ------------------------------------------------------------------ eval */
-static int eval_impl(bool dry, std::string *dump) {
+static int eval_impl(bool dry, std::string *dump, bool json = false) {
     EkContext &ctx = ek_ctx();
 
     if (!dry) for (auto cb : ctx.callbacks) cb.first(cb.second);         /* jit.cu:1421-1422 */
@@ -1288,7 +1288,42 @@ static int eval_impl(bool dry, std::string *dump) {
 
     if (dry) {
         std::ostringstream oss;
-        for (auto &l : launches) dump_program(oss, l.second, *l.first);
+        if (json) {
+            /* machine-readable form of the same listing for tests/ek_emulator.py (a numpy interpreter of the sweep ISA
+               that lets the CPU test-suite execute what the planner + assembler produce) */
+            oss << "{\"ops\":[";
+            for (int k = 0; k < DOP__COUNT; ++k) oss << (k ? "," : "") << "\"" << dop_name((uint16_t) k) << "\"";
+            oss << "],\"sweeps\":[";
+            bool first = true;
+            for (auto &l : launches) {
+                const Assembled &a = l.second;
+                oss << (first ? "" : ",") << "{\"phase\":" << l.first->phase << ",\"n\":" << l.first->size << ",\"n_tmp\":" << a.n_tmp;
+                first = false;
+                auto sec = [&](const char *name, const std::vector<EkInstr> &v) {
+                    oss << ",\"" << name << "\":[";
+                    for (size_t i = 0; i < v.size(); ++i)
+                        oss << (i ? "," : "") << "[" << v[i].op << "," << v[i].flags << "," << v[i].dst << "," << v[i].b << "," << v[i].c << "," << v[i].a << "," << v[i].imm << "]";
+                    oss << "]";
+                };
+                sec("init", a.init); sec("body", a.body); sec("fini", a.fini);
+                oss << ",\"lits\":[";
+                for (size_t i = 0; i < a.lits.size(); ++i) oss << (i ? "," : "") << a.lits[i];
+                oss << "],\"argw\":[";
+                for (size_t i = 0; i < a.argw.size(); ++i) oss << (i ? "," : "") << a.argw[i];
+                oss << "],\"ptr_fix\":[";
+                for (size_t i = 0; i < a.ptr_fix.size(); ++i) oss << (i ? "," : "") << "[" << a.ptr_fix[i].argw << "," << a.ptr_fix[i].var << "," << (a.ptr_fix[i].output ? 1 : 0) << "]";
+                oss << "],\"staged\":[";
+                for (size_t i = 0; i < a.staged.size(); ++i) oss << (i ? "," : "") << "[" << a.staged[i].var << "," << a.staged[i].unit << "," << (int) a.staged[i].esize << "]";
+                oss << "],\"scalars\":[";
+                for (size_t i = 0; i < a.scalars.size(); ++i) oss << (i ? "," : "") << "[" << a.scalars[i].var << "," << (int) ctx.vars[a.scalars[i].var].type << "]";
+                oss << "],\"outputs\":[";
+                for (size_t i = 0; i < a.outputs.size(); ++i) oss << (i ? "," : "") << "[" << a.outputs[i].var << "," << a.outputs[i].argw << "," << a.outputs[i].bytes << "," << (int) ctx.vars[a.outputs[i].var].type << "]";
+                oss << "]}";
+            }
+            oss << "]}";
+        } else {
+            for (auto &l : launches) dump_program(oss, l.second, *l.first);
+        }
         if (dump) *dump = oss.str();
         return 0;
     }
@@ -1479,6 +1514,13 @@ int ek_eval_var(uint32_t index) {
 EK_API char *ek_debug_plan(void) {
     std::string s;
     if (eval_impl(true, &s) != 0) return nullptr;
+    return strdup(s.c_str());
+}
+
+/* same as ek_debug_plan(), as JSON with the complete programs (tests/ek_emulator.py) */
+EK_API char *ek_debug_program(void) {
+    std::string s;
+    if (eval_impl(true, &s, true) != 0) return nullptr;
     return strdup(s.c_str());
 }
 
