@@ -115,6 +115,7 @@ SIGNATURES = {
     # debugging aid (host-only, not part of the reference-facing ABI)
     "ek_debug_plan": (c_vp, []),
     "ek_debug_program": (c_vp, []),
+    "ek_debug_discard_side_effects": (None, []),
 }
 
 _lib = None

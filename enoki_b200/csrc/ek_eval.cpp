@@ -1517,6 +1517,31 @@ EK_API char *ek_debug_plan(void) {
     return strdup(s.c_str());
 }
 
+/* host-only test aid: forget recorded scatters that can never run (CPU test-suite without a GPU), exactly as if they
+   had been executed: the trace's own reference is released and the node leaves the live set */
+EK_API void ek_debug_discard_side_effects(void) {
+    EkContext &ctx = ek_ctx();
+    std::vector<uint32_t> pending;
+    for (uint32_t idx : ctx.live)
+        if (idx < ctx.vars.size() && ctx.vars[idx].used && ctx.vars[idx].side_effect && ctx.vars[idx].op != EK_OP_INVALID) pending.push_back(idx);
+    for (uint32_t idx : pending) {
+        EkVariable &v = ctx.vars[idx];
+        v.side_effect = false;
+        v.op = EK_OP_INVALID;
+        uint32_t deps[4] = { v.dep[0], v.dep[1], v.dep[2], v.dep[3] };
+        uint32_t extra = v.extra_dep;
+        v.dep[0] = v.dep[1] = v.dep[2] = v.dep[3] = 0; v.extra_dep = 0;
+        for (int k = 0; k < 4; ++k) if (deps[k] >= EK_REG_RESERVED) {
+            EkVariable &d = ctx.vars[deps[k]];
+            if (d.used && d.ref_int > 0) { if (--d.ref_int == 0 && d.ref_ext == 0) { d.ref_ext = 1; ek_dec_ref_ext(deps[k]); } }
+        }
+        if (extra >= EK_REG_RESERVED) ek_dec_ref_ext(extra);
+        ek_dec_ref_ext(idx);
+    }
+    for (uint32_t idx : ctx.dirty) if (idx < ctx.vars.size()) ctx.vars[idx].dirty = false;
+    ctx.dirty.clear();
+}
+
 /* same as ek_debug_plan(), as JSON with the complete programs (tests/ek_emulator.py) */
 EK_API char *ek_debug_program(void) {
     std::string s;
