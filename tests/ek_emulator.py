@@ -1,16 +1,16 @@
 """numpy interpreter of the sweep ISA (enoki_b200/csrc/ek_isa.h) for the CPU test-suite: executes the programs that the
 planner + assembler produce (`enoki_b200.debug_program()`), so that scheduling, slot allocation, superinstruction
 fusion, reduction phases and operand encoding are checked on machines without a GPU.  TEST INFRASTRUCTURE: it mirrors
-what ek_sweep.cu does per element (32-bit value types only; 64-bit planes, gathers / scatters and the shared-memory
-helpers raise Unsupported) and uses the C oracle for the operations numpy cannot round identically (fma, Cephes)."""
+what ek_sweep.cu does per element (32- and 64-bit value types, the latter as lo/hi planes exactly like the kernel;
+gathers / scatters and the shared-memory helpers raise Unsupported) and uses the C oracle for the operations numpy cannot round identically (fma, Cephes)."""
 import ctypes
 
 import numpy as np
 
-F_ST, F_R64, F_HAS_B, F_HAS_C, F_HAS_A, F_NEG_A, F_ABS_A, F_STG, F_RACC = 1, 2, 4, 8, 0x80, 0x100, 0x200, 0x400, 0x4000
+F_ST, F_R64, F_HAS_B, F_HAS_C, F_B64, F_C64, F_A64, F_HAS_A, F_NEG_A, F_ABS_A, F_STG, F_RACC = 1, 2, 4, 8, 0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400, 0x4000
 OP_NONE = 0xFFFF
 SZ = ctypes.c_size_t
-T_FLOAT32, T_INT32, T_UINT32, T_BOOL = 10, 5, 6, 12
+T_FLOAT32, T_INT32, T_UINT32, T_BOOL, T_INT64, T_UINT64, T_FLOAT64 = 10, 5, 6, 12, 7, 8, 11
 
 
 class Unsupported(Exception):
@@ -48,6 +48,118 @@ class Emulator:
         self.oracle.or_minmax_f32(int(is_max), _P(a), _P(b), _P(out), SZ(len(a)))
         return self._u(out)
 
+    # ---- 64-bit values as (lo, hi) planes
+    @staticmethod
+    def _j(lo, hi): return (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+    @staticmethod
+    def _s(v):
+        v = np.ascontiguousarray(v).view(np.uint64)
+        return (v & np.uint64(0xffffffff)).astype(np.uint32), (v >> np.uint64(32)).astype(np.uint32)
+
+    def _unary64(self, which, x):
+        xf = np.ascontiguousarray(x.view(np.float64)); out = np.zeros_like(xf)
+        self.oracle.or_unary_f64(which, _P(xf), _P(out), SZ(len(xf)))
+        return out
+
+    def _exec64(self, name, imm, R, Rh, B, Bh, C, Ch, staged, cb):
+        """64-bit and width-changing operations; returns (lo, hi), "store", "ldg", or None if `name` is a 32-bit op."""
+        J, S = self._j, self._s
+        u = lambda lo, hi: J(lo, hi)
+        i = lambda lo, hi: J(lo, hi).view(np.int64)
+        d = lambda lo, hi: J(lo, hi).view(np.float64)
+        with np.errstate(all="ignore"):
+            if name == "LD_64": return S(staged[cb & 0x3fff])
+            if name == "LDG_64": return "ldg"
+            if name == "ST_64": return "store"
+            if name.endswith("_F64") and not name.startswith("CVT_"):
+                a = d(R, Rh); b = d(B, Bh) if Bh is not None else None; c = d(C, Ch) if Ch is not None else None
+                base = name[:-4]
+                if base in ("FMA", "FMAC"):
+                    x, y, z = (a, b, c) if base == "FMA" else (b, c, a)
+                    x, y, z = (np.ascontiguousarray(v) for v in (x, y, z)); out = np.zeros_like(x)
+                    self.oracle.or_fma_f64(_P(x), _P(y), _P(z), _P(out), SZ(len(x)))
+                    return S(out)
+                if base in ("MIN", "MAX", "MINR", "MAXR"):
+                    x, y = (a, b) if len(base) == 3 else (b, a)
+                    x, y = np.ascontiguousarray(x), np.ascontiguousarray(y); out = np.zeros_like(x)
+                    self.oracle.or_minmax_f64(int(base.startswith("MAX")), _P(x), _P(y), _P(out), SZ(len(x)))
+                    return S(out)
+                if base in ("LT", "LE", "GT", "GE", "EQ", "NE"):
+                    fn = {"LT": np.less, "LE": np.less_equal, "GT": np.greater, "GE": np.greater_equal, "EQ": np.equal, "NE": np.not_equal}[base]
+                    return fn(a, b).astype(np.uint32), Rh
+                r = {"ADD": lambda: a + b, "SUB": lambda: a - b, "SUBR": lambda: b - a, "MUL": lambda: a * b, "DIV": lambda: a / b,
+                     "DIVR": lambda: b / a, "ABS": lambda: np.abs(a), "NEG": lambda: -a, "SQRT": lambda: np.sqrt(a),
+                     "FLOOR": lambda: np.floor(a), "CEIL": lambda: np.ceil(a), "ROUND": lambda: np.rint(a), "TRUNC": lambda: np.trunc(a),
+                     "EXP": lambda: self._unary64(2, a), "LOG": lambda: self._unary64(3, a), "SIN": lambda: self._unary64(0, a),
+                     "COS": lambda: self._unary64(1, a)}.get(base)
+                if r is None:
+                    raise Unsupported(name)
+                return S(np.ascontiguousarray(r()))
+            if name.endswith(("_I64", "_U64", "_64")) and not name.startswith("CVT_"):
+                signed = name.endswith("_I64")
+                a = i(R, Rh) if signed else u(R, Rh)
+                b = (i(B, Bh) if signed else u(B, Bh)) if Bh is not None else None
+                base = name.rsplit("_", 1)[0]
+                if base in ("SHL", "SHR"):                              # the count is the 32-bit low plane only
+                    cnt = B.astype(np.uint64)
+                    if base == "SHL": return S(np.where(cnt >= 64, np.uint64(0), u(R, Rh) << (cnt & np.uint64(63))))
+                    if signed: return S((i(R, Rh) >> np.minimum(cnt, np.uint64(63)).astype(np.int64)).view(np.uint64))
+                    return S(np.where(cnt >= 64, np.uint64(0), u(R, Rh) >> (cnt & np.uint64(63))))
+                if base in ("SHLR", "SHRR"):
+                    val = i(B, Bh) if signed else u(B, Bh); cnt = R.astype(np.uint64)
+                    if base == "SHLR": return S(np.where(cnt >= 64, np.uint64(0), u(B, Bh) << (cnt & np.uint64(63))))
+                    if signed: return S((val >> np.minimum(cnt, np.uint64(63)).astype(np.int64)).view(np.uint64))
+                    return S(np.where(cnt >= 64, np.uint64(0), val >> (cnt & np.uint64(63))))
+                if base in ("LT", "LE", "GT", "GE"):
+                    fn = {"LT": np.less, "LE": np.less_equal, "GT": np.greater, "GE": np.greater_equal}[base]
+                    return fn(a, b).astype(np.uint32), Rh
+                if base == "EQ": return (u(R, Rh) == u(B, Bh)).astype(np.uint32), Rh
+                if base == "NE": return (u(R, Rh) != u(B, Bh)).astype(np.uint32), Rh
+                if base == "SEL_M": return np.where(R != 0, B, C), np.where(R != 0, Bh, Ch)
+                if base == "SEL_T": return np.where(B != 0, R, C), np.where(B != 0, Rh, Ch)
+                if base == "SEL_F": return np.where(B != 0, C, R), np.where(B != 0, Ch, Rh)
+                if base == "LOAD": return B, Bh
+                ua, ub = u(R, Rh), (u(B, Bh) if Bh is not None else None)
+                r = {"ADD": lambda: ua + ub, "SUB": lambda: ua - ub, "SUBR": lambda: ub - ua, "MUL": lambda: ua * ub,
+                     "MAD": lambda: ua * ub + u(C, Ch), "MADC": lambda: ub * u(C, Ch) + ua,
+                     "MIN": lambda: np.minimum(a, b).view(np.uint64), "MAX": lambda: np.maximum(a, b).view(np.uint64),
+                     "ABS": lambda: np.where(i(R, Rh) < 0, np.uint64(0) - ua, ua), "NEG": lambda: np.uint64(0) - ua,
+                     "NOT": lambda: ~ua, "AND": lambda: ua & ub, "OR": lambda: ua | ub, "XOR": lambda: ua ^ ub}.get(base)
+                if r is None:
+                    raise Unsupported(name)
+                return S(np.ascontiguousarray(r()))
+            if name.startswith("CVT_"):
+                f32 = R.view(np.float32)
+                if name == "CVT_I32_I64": return R, (R.view(np.int32) >> 31).view(np.uint32)
+                if name == "CVT_U32_U64": return R, np.zeros_like(R)
+                if name == "CVT_64_32": return R, Rh
+                if name == "CVT_F32_F64": return S(f32.astype(np.float64))
+                if name == "CVT_F64_F32": return d(R, Rh).astype(np.float32).view(np.uint32), Rh
+                if name == "CVT_I32_F64": return S(R.view(np.int32).astype(np.float64))
+                if name == "CVT_U32_F64": return S(R.astype(np.float64))
+                if name == "CVT_I64_F64": return S(i(R, Rh).astype(np.float64))
+                if name == "CVT_U64_F64": return S(u(R, Rh).astype(np.float64))
+                if name == "CVT_I64_F32": return i(R, Rh).astype(np.float32).view(np.uint32), Rh
+                if name == "CVT_U64_F32": return u(R, Rh).astype(np.float32).view(np.uint32), Rh
+                if name in ("CVT_F64_I64", "CVT_F64_U64", "CVT_F32_I64", "CVT_F32_U64"):
+                    if imm != 0:
+                        raise Unsupported("rounded conversion")
+                    x = d(R, Rh) if "F64" in name else f32.astype(np.float64)
+                    ok = (x >= -9.2233720368547758e18) & (x < 9.2233720368547758e18)
+                    return S(np.where(ok, np.trunc(np.where(ok, x, 0)).astype(np.int64), np.int64(-9223372036854775808)).view(np.uint64))
+                if name in ("CVT_F64_I32",):
+                    x = d(R, Rh); ok = (x >= -2147483648.0) & (x < 2147483648.0)
+                    r = {0: np.trunc, 1: np.floor, 2: np.ceil, 3: np.rint}[imm](x)
+                    return np.where(ok, np.where(ok, r, 0).astype(np.int64), np.int64(-2147483648)).astype(np.int32).view(np.uint32), Rh
+                if name == "CVT_F64_U32":
+                    if imm != 0:
+                        raise Unsupported("rounded conversion")
+                    x = d(R, Rh); ok = (x >= -9.2233720368547758e18) & (x < 9.2233720368547758e18)
+                    v = np.where(ok, np.trunc(np.where(ok, x, 0)).astype(np.int64), np.int64(-9223372036854775808))
+                    return (v.view(np.uint64) & np.uint64(0xffffffff)).astype(np.uint32), Rh
+                return None                                       # 32-bit conversions are handled by the caller
+        return None
+
     def run(self, program):
         names = program["ops"]
         for sw in program["sweeps"]:
@@ -65,19 +177,24 @@ class Emulator:
         for var, typ in sw["scalars"]:
             v = self.vars[var]
             if v.dtype.itemsize == 8:
-                raise Unsupported("64-bit scalar")
+                bits = int(v.reshape(-1).view(np.uint64)[0])
+                uni += [np.uint32(bits & 0xffffffff), np.uint32(bits >> 32)]
+                continue
             lo = np.uint32(1 if (typ == T_BOOL and v.reshape(-1)[0]) else v.reshape(-1).view(np.uint32 if v.dtype.itemsize == 4 else v.dtype)[0])
             uni += [lo, np.uint32(0)]
         staged = {}
         for var, unit, es in sw["staged"]:
-            if es != 4:
-                raise Unsupported("staged input of element size %d" % es)
             a = self.vars[var]
             assert a.size == n, (var, a.size, n)
-            staged[unit] = self._u(a)
+            if es == 4:
+                staged[unit] = self._u(a)
+            elif es == 8:
+                staged[unit] = np.ascontiguousarray(a).view(np.uint64)        # unpacked by LD_64
+            else:
+                raise Unsupported("staged input of element size %d" % es)
         out_type = {var: typ for var, _aw, _bytes, typ in sw["outputs"]}
         slots = {}
-        state = {"R": np.zeros(n, np.uint32)}
+        state = {"R": np.zeros(n, np.uint32), "Rh": np.zeros(n, np.uint32)}
         idx = np.arange(n, dtype=np.uint32)
 
         def bcast(v):
@@ -99,6 +216,15 @@ class Emulator:
                 raise AssertionError("read of slot %d before it was written" % code)
             return slots[code].copy()
 
+        def fetch_hi(code):
+            if code & 0x8000:
+                return bcast(uni[(code & 0x3fff) + 1])
+            if code & 0x4000:
+                raise AssertionError("high plane of a staged operand")
+            if code + 1 not in slots:
+                raise AssertionError("read of the high plane of slot %d before it was written" % code)
+            return slots[code + 1].copy()
+
         def var_of_uniform(ui):
             aw = ui - n_lit
             assert 0 <= aw < n_arg and aw in ptr, ("uniform index is not a pointer argument", ui)
@@ -114,6 +240,9 @@ class Emulator:
                 self.vars[var] = R.view(np.int32).copy()
             elif typ == T_UINT32:
                 self.vars[var] = R.copy()
+            elif typ in (T_INT64, T_UINT64, T_FLOAT64):
+                v = self._j(R, state["Rh"])
+                self.vars[var] = v.view({T_INT64: np.int64, T_UINT64: np.uint64, T_FLOAT64: np.float64}[typ]).copy()
             else:
                 raise Unsupported("output type %d" % typ)
 
@@ -157,10 +286,10 @@ class Emulator:
         def execute(ins):
             op, flags, dst, cb, cc, ca, imm = ins
             name = names[op]
-            if flags & F_R64:
-                raise Unsupported("64-bit value")
             if flags & F_HAS_A:
                 state["R"] = fetch(ca)
+                if flags & F_A64:
+                    state["Rh"] = fetch_hi(ca)
             if flags & F_ABS_A:
                 state["R"] = state["R"] & np.uint32(0x7fffffff)
             if flags & F_NEG_A:
@@ -168,7 +297,29 @@ class Emulator:
             R = state["R"]
             B = fetch(cb) if flags & F_HAS_B else None
             C = fetch(cc) if flags & F_HAS_C else None
+            Bh = fetch_hi(cb) if flags & F_B64 else None
+            Ch = fetch_hi(cc) if flags & F_C64 else None
+            Rh = state["Rh"]
             f = self._f
+            if name.endswith(("_F64", "_I64", "_U64", "_64")) or name.startswith(("CVT_", "LD_64", "LDG_64", "ST_64")):
+                handled = self._exec64(name, imm, R, Rh, B, Bh, C, Ch, staged, cb)
+                if handled is not None:
+                    if handled == "store":
+                        store_var(var_of_uniform(imm), R); return
+                    if handled == "ldg":
+                        v = np.ascontiguousarray(self.vars[var_of_uniform(imm)]).view(np.uint64)
+                        state["R"], state["Rh"] = self._s(v)
+                    else:
+                        state["R"], state["Rh"] = handled
+                    if flags & F_RACC:
+                        racc(dst, ca)
+                    if flags & F_STG:
+                        store_var(var_of_uniform(imm), state["R"])
+                    if flags & F_ST:
+                        slots[dst] = state["R"].copy()
+                        if flags & F_R64:
+                            slots[dst + 1] = state["Rh"].copy()
+                    return
             with np.errstate(all="ignore"):
                 if name == "NOP": pass
                 elif name == "ADD_F32": R = self._u(f(R) + f(B))
@@ -252,6 +403,8 @@ class Emulator:
                 store_var(var_of_uniform(imm), state["R"])
             if flags & F_ST:
                 slots[dst] = state["R"].copy()
+                if flags & F_R64:
+                    slots[dst + 1] = state["Rh"].copy()
 
         for ins in sw["init"]:
             execute(ins)

@@ -81,3 +81,103 @@ def test_random_expression_dags_on_the_emulator(ek, oracle, P, seed):
     gc.collect()
     if reason:
         pytest.skip(reason)
+
+
+# ------------------------------------------------------------------ 64-bit values (lo / hi planes)
+def _build64(EK, oracle, P, rng, n, n_nodes, data):
+    M = fuzz.Mirror
+    D, U, I = EK.Float64, EK.UInt64, EK.Int64
+    dl = [M(D.copy(a), a) for a in data["f64"]]
+    ul = [M(U.copy(a), a) for a in data["u64"]]
+    fl = [M(EK.Float32.copy(a), a) for a in data["f32"]]
+    SZ = fuzz.SZ
+    bc = lambda a: np.ascontiguousarray(np.broadcast_to(a, (n,)) if a.shape[0] == 1 else a)
+
+    def orc_unary(which, x):
+        x = np.ascontiguousarray(x); out = np.zeros_like(x)
+        oracle.or_unary_f64(which, P(x), P(out), SZ(len(x))); return out
+    for _ in range(n_nodes):
+        kind = rng.integers(0, 15)
+        a, b, c = (dl[rng.integers(len(dl))] for _ in range(3))
+        u, v = (ul[rng.integers(len(ul))] for _ in range(2))
+        with np.errstate(all="ignore"):
+            if kind == 0: dl.append(M(a.e + b.e, a.n + b.n))
+            elif kind == 1: dl.append(M(a.e * b.e - c.e, a.n * b.n - c.n))
+            elif kind == 2:
+                an, bn, cn = bc(a.n), bc(b.n), bc(c.n); out = np.zeros(n)
+                oracle.or_fma_f64(P(an), P(bn), P(cn), P(out), SZ(n))
+                dl.append(M(EK.fmadd(a.e, b.e, c.e), out if max(len(a.n), len(b.n), len(c.n)) > 1 else out[:1]))
+            elif kind == 3: dl.append(M(EK.sqrt(abs(a.e)), np.sqrt(np.abs(a.n))))
+            elif kind == 4:
+                which, fn = ((0, EK.sin), (2, EK.exp))[rng.integers(2)]
+                dl.append(M(fn(a.e), orc_unary(which, a.n)))
+            elif kind == 5: dl.append(M(EK.select(a.e < b.e, a.e, -c.e), np.where(a.n < b.n, a.n, -c.n)))
+            elif kind == 6: dl.append(M(EK.floor(a.e), np.floor(a.n)))
+            elif kind == 7: ul.append(M(u.e + v.e * U(3), u.n + v.n * np.uint64(3)))
+            elif kind == 8: ul.append(M((u.e ^ v.e) | (u.e & v.e), (u.n ^ v.n) | (u.n & v.n)))
+            elif kind == 9:
+                s = int(rng.integers(1, 63))
+                ul.append(M((u.e << U(s)) | (v.e >> U(s)), (u.n << np.uint64(s)) | (v.n >> np.uint64(s))))
+            elif kind == 10: ul.append(M(EK.select(u.e < v.e, u.e, v.e), np.where(u.n < v.n, u.n, v.n)))
+            elif kind == 11:                                    # u64 -> f64 -> scaled -> i64 -> u64 (bounded)
+                x = D(u.e >> U(20)) * D(0.5); xn = (u.n >> np.uint64(20)).astype(np.float64) * 0.5
+                dl.append(M(x, xn))
+                ul.append(M(U(I(x)), np.trunc(xn).astype(np.int64).view(np.uint64)))
+            elif kind == 12:                                    # narrowing and widening
+                ul.append(M(U(EK.UInt32(u.e)) + v.e, (u.n & np.uint64(0xffffffff)) + v.n))
+            elif kind == 13:                                    # f32 <-> f64
+                g = fl[rng.integers(len(fl))]
+                dl.append(M(D(g.e) * a.e, g.n.astype(np.float64) * a.n))
+                fl.append(M(EK.Float32(a.e), a.n.astype(np.float32)))
+            elif kind == 14: ul.append(M(u.e - v.e, u.n - v.n))
+    return dl, ul, fl
+
+
+def _case64(ek, oracle, P, seed):
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.choice([1, 33, 1000, 4097]))
+    data = {"f64": [rng.uniform(-4, 4, n) for _ in range(3)] + [np.array([rng.uniform(-2, 2)])],
+            "u64": [rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + np.uint64(rng.integers(2)) for _ in range(2)] + [np.array([rng.integers(1, 100)], np.uint64)],
+            "f32": [rng.uniform(-4, 4, n).astype(np.float32)]}
+    table = {}
+
+    class EK:
+        Float32 = _Factory(ek.Float32, table, 0x7f0000000000)
+        UInt32 = _Factory(ek.UInt32, table, 0x7a0000000000)
+        Float64 = _Factory(ek.Float64, table, 0x790000000000)
+        UInt64 = _Factory(ek.UInt64, table, 0x780000000000)
+        Int64 = _Factory(ek.Int64, table, 0x770000000000)
+        fmadd, max_, min_, sqrt, floor, sin, exp, select = ek.fmadd, ek.max_, ek.min_, ek.sqrt, ek.floor, ek.sin, ek.exp, ek.select
+
+    dl, ul, fl = _build64(EK, oracle, P, rng, n, int(rng.integers(6, 30)), data)
+    keep = [dl[k] for k in rng.choice(len(dl), size=min(3, len(dl)), replace=False)] + \
+           [ul[k] for k in rng.choice(len(ul), size=min(3, len(ul)), replace=False)] + [fl[-1]]
+    del dl, ul, fl
+    emu = Emulator(oracle, table)
+    try:
+        emu.run(ek.debug_program())
+    except Unsupported as e:
+        return f"emulator: {e}"
+    for m in keep:
+        if m.e.index not in emu.vars:
+            raise AssertionError(f"variable {m.e.index} was not produced by any sweep")
+        got = emu.vars[m.e.index]; want = np.broadcast_to(m.n, got.shape).astype(got.dtype)
+        bits = np.uint64 if got.dtype.itemsize == 8 else np.uint32
+        same = got.view(bits) == np.ascontiguousarray(want).view(bits)
+        if got.dtype.kind == "f":
+            same |= np.isnan(got) & np.isnan(want)
+        assert same.all(), (seed, n, got.dtype, got[~same][:3], want[~same][:3])
+    return None
+
+
+@pytest.mark.parametrize("seed", range(100))
+def test_random_64bit_dags_on_the_emulator(ek, oracle, P, seed):
+    import gc
+    gc.collect()
+    ek.lib().ek_debug_discard_side_effects()
+    gc.collect()
+    assert ek.debug_plan() == "", "unevaluated variables of an earlier test are still alive"
+    reason = _case64(ek, oracle, P, seed)
+    gc.collect()
+    if reason:
+        pytest.skip(reason)
