@@ -445,6 +445,30 @@ def main():
     if rank == 0:
         hist = bench_histogram(ek, L, n, peak_gbs)
 
+    # ---- launch-latency regime: the same C2 expression on 2^20 elements
+    small = None
+    if rank == 0:
+        ns = 1 << 20
+        xs_s = [Float32.copy(np.random.default_rng(k).uniform(-4, 4, ns).astype(np.float32)) for k in range(4)]
+
+        def small_step():
+            t = fmadd(xs_s[0], xs_s[1], xs_s[2])
+            o = fmadd(sin(fmadd(xs_s[3], exp(-(t * t)), xs_s[0])), xs_s[1], sqrt(abs(t)))
+            del t
+            ek.cuda_eval()
+            return o
+        for _ in range(5):
+            small_step()
+        ek.cuda_sync()
+        L.ek_timer_start()
+        reps_s = 200
+        for _ in range(reps_s):
+            small_step()
+        ms_s = L.ek_timer_stop() / reps_s
+        small = {"workload": "C2 on 2^20 elements (launch-latency regime)", "ms_per_step": ms_s,
+                 "m_array_ops_per_s": ns * C2_NODES / (ms_s * 1e-3) / 1e6}
+        del xs_s
+
     # ---- backward: C4 tape (per rank), K' passes of backward(free_graph=False)
     backward = None
     if not args.skip_backward:
@@ -472,7 +496,7 @@ def main():
                        "l2": "inputs 4 x 256 MiB per step exceed the 126 MB L2 (no explicit flush needed)",
                        "parallelism": f"element-range sharding x{world}, one rank per GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "backward": backward, "histogram": hist, "wall_ms_per_step": wall_ms / args.steps, "loss_checksum": loss_val,
+            "backward": backward, "histogram": hist, "small": small, "wall_ms_per_step": wall_ms / args.steps, "loss_checksum": loss_val,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -5,6 +5,6 @@ python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_final.json")); r = json.load(open("gpurun_out/bench_ref_final.json"))
 print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"], d["backward"]["roofline"]["frac"], d["histogram"]["kernel_ms"], d["clocks"])
-print(d["cpu_baseline"])
+print(d["cpu_baseline"]); print(d.get("small"))
 print(r["value"], r["ms_per_step"], r["cpu_baseline"]["cores"], r["cpu_baseline"]["sample"][:70])
 PY
