@@ -16,6 +16,9 @@ The JSON line also carries
   backward      -- the C4 tape (10 240 nodes / 20 224 edges, node width 131 072): M edge-adjoints/s
   e2e           -- same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timing)
   cpu_baseline  -- the reference's own CPU path (oracle/_ref) timed on this box's host cores
+  histogram     -- C3 (configs[2]): 2^26-sample gather + scatter_add histogram, kernel time
+  small         -- the C2 expression on 2^20 elements (launch-latency regime)
+  clocks        -- nvidia-smi SM clock / throttle reasons sampled inside the timed window
 `--impl reference` times the reference CPU path alone (rank 0 only).
 """
 import argparse
