@@ -181,3 +181,41 @@ def test_random_64bit_dags_on_the_emulator(ek, oracle, P, seed):
     gc.collect()
     if reason:
         pytest.skip(reason)
+
+
+def _case_many_outputs(ek, oracle, P):
+    """More live results than one kernel has slots / arguments for: the planner splits the group and recomputes shared
+    sub-expressions (as the reference does across kernels); every output must still be right."""
+    rng = np.random.default_rng(77)
+    n = 1000
+    table = {}
+    F = _Factory(ek.Float32, table, 0x7f0000000000)
+    xs = [rng.uniform(-2, 2, n).astype(np.float32) for _ in range(6)]
+    X = [F.copy(a) for a in xs]
+    outs, want = [], []
+    base_e = ek.fmadd(X[0], X[1], X[2]); base_n = None
+    an, bn, cn = xs[0], xs[1], xs[2]
+    base_n = np.zeros(n, np.float32); oracle.or_fma_f32(P(an), P(bn), P(cn), P(base_n), fuzz.SZ(n))
+    for k in range(48):
+        a = X[k % 6]; an = xs[k % 6]
+        e = (base_e + a) * ek.Float32(float(k + 1)) - X[(k + 3) % 6]
+        w = ((base_n + an) * np.float32(k + 1) - xs[(k + 3) % 6]).astype(np.float32)
+        outs.append(e); want.append(w)
+    del base_e
+    prog = ek.debug_program()
+    n_sweeps = len(prog["sweeps"])
+    emu = Emulator(oracle, table)
+    emu.run(prog)
+    for e, w in zip(outs, want):
+        got = emu.vars[e.index]
+        assert (got.view(np.uint32) == w.view(np.uint32)).all()
+    return n_sweeps
+
+
+def test_group_splitting_on_the_emulator(ek, oracle, P):
+    import gc
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    assert ek.debug_plan() == ""
+    n_sweeps = _case_many_outputs(ek, oracle, P)
+    gc.collect()
+    assert n_sweeps >= 1
