@@ -196,7 +196,7 @@ def _case_many_outputs(ek, oracle, P):
     base_e = ek.fmadd(X[0], X[1], X[2]); base_n = None
     an, bn, cn = xs[0], xs[1], xs[2]
     base_n = np.zeros(n, np.float32); oracle.or_fma_f32(P(an), P(bn), P(cn), P(base_n), fuzz.SZ(n))
-    for k in range(48):
+    for k in range(300):
         a = X[k % 6]; an = xs[k % 6]
         e = (base_e + a) * ek.Float32(float(k + 1)) - X[(k + 3) % 6]
         w = ((base_n + an) * np.float32(k + 1) - xs[(k + 3) % 6]).astype(np.float32)
@@ -218,4 +218,4 @@ def test_group_splitting_on_the_emulator(ek, oracle, P):
     assert ek.debug_plan() == ""
     n_sweeps = _case_many_outputs(ek, oracle, P)
     gc.collect()
-    assert n_sweeps >= 1
+    assert n_sweeps >= 2            # 300 outputs do not fit one kernel's argument words: the group was split
