@@ -1311,7 +1311,7 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
                 oss << "],\"argw\":[";
                 for (size_t i = 0; i < a.argw.size(); ++i) oss << (i ? "," : "") << a.argw[i];
                 oss << "],\"ptr_fix\":[";
-                for (size_t i = 0; i < a.ptr_fix.size(); ++i) oss << (i ? "," : "") << "[" << a.ptr_fix[i].argw << "," << a.ptr_fix[i].var << "," << (a.ptr_fix[i].output ? 1 : 0) << "]";
+                for (size_t i = 0; i < a.ptr_fix.size(); ++i) oss << (i ? "," : "") << "[" << a.ptr_fix[i].argw << "," << a.ptr_fix[i].var << "," << (a.ptr_fix[i].output ? 1 : 0) << "," << (unsigned long long) (uintptr_t) ctx.vars[a.ptr_fix[i].var].data << "]";
                 oss << "],\"staged\":[";
                 for (size_t i = 0; i < a.staged.size(); ++i) oss << (i ? "," : "") << "[" << a.staged[i].var << "," << a.staged[i].unit << "," << (int) a.staged[i].esize << "]";
                 oss << "],\"scalars\":[";

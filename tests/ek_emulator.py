@@ -2,7 +2,8 @@
 planner + assembler produce (`enoki_b200.debug_program()`), so that scheduling, slot allocation, superinstruction
 fusion, reduction phases and operand encoding are checked on machines without a GPU.  TEST INFRASTRUCTURE: it mirrors
 what ek_sweep.cu does per element (32- and 64-bit value types, the latter as lo/hi planes exactly like the kernel;
-gathers / scatters and the shared-memory helpers raise Unsupported) and uses the C oracle for the operations numpy cannot round identically (fma, Cephes)."""
+32-bit gathers / scatters incl. the shared-memory table / privatised-bin helpers; float scatter_add is accumulated in
+element order, so compare it with a tolerance) and uses the C oracle for the operations numpy cannot round identically (fma, Cephes)."""
 import ctypes
 
 import numpy as np
@@ -22,10 +23,12 @@ def _P(a):
 
 
 class Emulator:
-    def __init__(self, oracle, arrays):
-        """arrays: variable index -> numpy array (uint32 / int32 / float32 / bool data of evaluated inputs)."""
+    def __init__(self, oracle, arrays, by_address=None):
+        """arrays: variable index -> numpy array (data of evaluated inputs); by_address: device address -> variable index
+        (gather sources / scatter targets reach the program as raw pointers, not as variables)."""
         self.oracle = oracle
         self.vars = {k: np.ascontiguousarray(v) for k, v in arrays.items()}
+        self.by_address = dict(by_address or {})
 
     # ---- helpers
     @staticmethod
@@ -170,8 +173,8 @@ class Emulator:
         lits, argw = sw["lits"], list(sw["argw"])
         n_lit, n_arg = len(lits), len(argw)
         ptr = {}                                    # argw index -> variable
-        for aw, var, _out in sw["ptr_fix"]:
-            ptr[aw] = var
+        for aw, var, _out, address in sw["ptr_fix"]:
+            ptr[aw] = self.by_address.get(address, var) if var not in self.vars else var
         # uniform pool = literals | argument words | scalar (lo, hi) pairs
         uni = [np.uint32(v) for v in lits] + [None] * n_arg
         for var, typ in sw["scalars"]:
@@ -194,7 +197,20 @@ class Emulator:
                 raise Unsupported("staged input of element size %d" % es)
         out_type = {var: typ for var, _aw, _bytes, typ in sw["outputs"]}
         slots = {}
+        smem = {}                                   # descriptor uniform index -> staged table / privatised bins
         state = {"R": np.zeros(n, np.uint32), "Rh": np.zeros(n, np.uint32)}
+
+        def desc(ui):                               # {smem_off, count, copies, uniform index of the pointer}
+            di = ui - n_lit
+            return argw[di + 1], ptr[argw[di + 3] - n_lit]
+
+        def gs_target(imm):                         # global gather / scatter: imm = uniform | stride << 16 | signed << 31
+            var = var_of_uniform(imm & 0xffff)
+            stride = (imm >> 16) & 0x7fff
+            if stride != 4:
+                raise Unsupported("gather/scatter stride %d" % stride)
+            return var
+
         idx = np.arange(n, dtype=np.uint32)
 
         def bcast(v):
@@ -392,6 +408,39 @@ class Emulator:
                 elif name == "CVT_U32_F32": R = self._u(R.astype(np.float32))
                 elif name == "LDG_32": R = self._u(self.vars[var_of_uniform(imm)]).copy()
                 elif name == "ST_32": store_var(var_of_uniform(imm), R)
+                elif name == "SMEM_ZERO":
+                    cnt, _var = desc(imm); smem[imm] = np.zeros(cnt, np.uint32); return
+                elif name == "SMEM_LOAD_TABLE":
+                    cnt, var = desc(imm); smem[imm] = self._u(self.vars[var])[:cnt].copy(); return
+                elif name in ("SMEM_FLUSH_ADD_F32", "SMEM_FLUSH_ADD_I32"):
+                    cnt, var = desc(imm)
+                    tgt = self._u(self.vars[var]).copy()
+                    if name.endswith("F32"): tgt[:cnt] = self._u(f(tgt[:cnt]) + f(smem[imm]))
+                    else: tgt[:cnt] = tgt[:cnt] + smem[imm]
+                    self.vars[var] = tgt.view(self.vars[var].dtype)
+                    return
+                elif name == "GATHER_32_SMEM":
+                    tab = smem[imm]; m = (B != 0) & (R < len(tab))
+                    R = np.where(m, tab[np.where(m, R, 0)], np.uint32(0))
+                elif name == "GATHER_32":
+                    src = self._u(self.vars[gs_target(imm)]); m = (B != 0) & (R < len(src))
+                    R = np.where(m, src[np.where(m, R, 0)], np.uint32(0))
+                elif name in ("SCATTER_ADD_F32_SMEM", "SCATTER_ADD_I32_SMEM", "SCATTER_ADD_F32", "SCATTER_ADD_I32", "SCATTER_32"):
+                    if name.endswith("_SMEM"):
+                        tgt = smem[imm]
+                    else:
+                        var = gs_target(imm); tgt = self._u(self.vars[var]).copy()
+                    m = (C != 0) & (R < len(tgt))
+                    ii, vv = R[m], B[m]
+                    if name == "SCATTER_32": tgt[ii] = vv
+                    elif "F32" in name:
+                        tf = tgt.view(np.float32)
+                        for k_, v_ in zip(ii.tolist(), vv.view(np.float32).tolist()):      # element order, one rounding each
+                            tf[k_] = np.float32(tf[k_] + np.float32(v_))
+                    else: np.add.at(tgt, ii, vv)
+                    if not name.endswith("_SMEM"):
+                        self.vars[var] = tgt.view(self.vars[var].dtype)
+                    return
                 elif name == "RACC": state["R"] = R; racc(dst, imm); return
                 elif name == "RFIN": rfin(B, imm, dst); return
                 else:

@@ -12,9 +12,13 @@ class _Factory:
     def __init__(self, cls, table, base):
         self.cls, self.table, self.base = cls, table, base
 
+    addresses = {}                              # device address -> variable index (all factories)
+
     def copy(self, a):
-        r = self.cls.map(self.base + 0x1000000 * (len(self.table) + 1), len(a))
+        address = self.base + 0x1000000 * (len(self.table) + 1)
+        r = self.cls.map(address, len(a))
         self.table[r.index] = np.ascontiguousarray(a)
+        _Factory.addresses[address] = r.index
         return r
 
     def __call__(self, *args):
@@ -219,3 +223,51 @@ def test_group_splitting_on_the_emulator(ek, oracle, P):
     n_sweeps = _case_many_outputs(ek, oracle, P)
     gc.collect()
     assert n_sweeps >= 2            # 300 outputs do not fit one kernel's argument words: the group was split
+
+
+def _case_histogram(ek, oracle, P, n_bins, n):
+    """C3 shape (tests/histogram.cpp:41-57): idx = UInt32((y + 4) * n_bins / 8); mask = idx < n_bins;
+    w = gather(table, idx, mask); scatter_add(bins_u32, 1, idx, mask); scatter_add(hist_f32, w, idx, mask)."""
+    from enoki_b200 import Float32, UInt32, gather, scatter_add
+    rng = np.random.default_rng(n_bins)
+    table = {}
+    F = _Factory(Float32, table, 0x7f0000000000); U = _Factory(UInt32, table, 0x7a0000000000)
+    y_n = rng.normal(0, 1.3, n).astype(np.float32)
+    tab_n = np.linspace(0.5, 1.5, n_bins, dtype=np.float32)
+    y = F.copy(y_n); tab = F.copy(tab_n)
+    bins = U.copy(np.zeros(n_bins, np.uint32)); hist = F.copy(np.zeros(n_bins, np.float32))
+    idx = UInt32((y + 4.0) * float(n_bins) / 8.0)
+    mask = idx < UInt32(n_bins)
+    w = gather(Float32, tab, idx, mask)
+    scatter_add(bins, UInt32(1), idx, mask)
+    scatter_add(hist, w, idx, mask)
+    del idx, mask, w
+    plan = ek.debug_plan()
+    emu = Emulator(oracle, table, _Factory.addresses)
+    emu.run(ek.debug_program())
+    with np.errstate(all="ignore"):
+        t = ((y_n + np.float32(4.0)) * np.float32(n_bins)) / np.float32(8.0)
+        ok = (t > -9.2e18) & (t < 9.2e18)
+        idx_n = np.where(ok, np.trunc(np.where(ok, t, 0)).astype(np.int64) & 0xffffffff, 0).astype(np.uint32)
+    m = idx_n < n_bins
+    want_bins = np.bincount(idx_n[m], minlength=n_bins).astype(np.uint32)
+    want_hist = np.bincount(idx_n[m], weights=tab_n[idx_n[m]].astype(np.float64), minlength=n_bins)
+    got_bins = emu.vars[bins.index].view(np.uint32); got_hist = emu.vars[hist.index].view(np.float32)
+    assert (got_bins == want_bins).all()
+    assert np.allclose(got_hist, want_hist, rtol=1e-4, atol=1e-3)
+    ek.lib().ek_debug_discard_side_effects()
+    return plan
+
+
+@pytest.mark.parametrize("n_bins,n", [(31, 5000), (700, 4000), (5000, 3000)])
+def test_histogram_programs_on_the_emulator(ek, oracle, P, n_bins, n):
+    """31 and 700 bins use shared-memory bins (+ a staged table for 31); 5000 bins go to global atomics."""
+    import gc
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    assert ek.debug_plan() == ""
+    plan = _case_histogram(ek, oracle, P, n_bins, n)
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    if n_bins <= 1024:
+        assert "SCATTER_ADD_I32_SMEM" in plan and "SMEM_FLUSH_ADD_I32" in plan
+    else:
+        assert "SCATTER_ADD_I32 " in plan and "SMEM_ZERO" not in plan
