@@ -160,3 +160,47 @@ def test_tape_bookkeeping_cpu(ek):
     assert lib.ek_tape_node_count(F32) == 0
     zero = (ctypes.c_uint32 * 1)(0)
     assert lib.ek_tape_append(F32, b"mul", 8, 1, zero, wh) == 0   # no differentiable input -> index 0
+
+
+def test_simplify_graph_structure_cpu(ek):
+    """Greedy vertex elimination (autodiff.cpp:990-1074) is host logic: interior nodes of a chain / a diamond are
+    collapsed, their edge weights become traced products (mul_nz / fma_nz), nodes that are still referenced from
+    outside stay.  No GPU needed: simplification only records trace nodes."""
+    import ctypes
+    lib = ek.lib()
+    F32 = ek.EK_FLOAT32
+    n = 64
+
+    def weight(k):
+        return ek.Float32.map(0x7b0000000000 + 0x100000 * k, n)
+
+    def node(label, srcs, ws):
+        idx = (ctypes.c_uint32 * len(srcs))(*srcs); wh = (ctypes.c_uint32 * len(ws))(*[w.index for w in ws])
+        h = lib.ek_tape_append(F32, label, n, len(srcs), idx, wh)
+        assert h
+        return h
+    assert lib.ek_tape_node_count(F32) == 0
+    ws = [weight(k) for k in range(8)]
+    leaf = lib.ek_tape_append_leaf(F32, n)
+    a = node(b"a", [leaf], [ws[0]])
+    b = node(b"b", [a], [ws[1]])
+    c = node(b"c", [b], [ws[2]])
+    # diamond on top of the chain: d = f(c, c') with c' = g(c)
+    c2 = node(b"c2", [c], [ws[3]])
+    d = node(b"d", [c, c2], [ws[4], ws[5]])
+    for h in (a, b, c, c2):                     # interior nodes lose their external references
+        lib.ek_tape_dec_ref_ext(F32, h)
+    assert lib.ek_tape_node_count(F32) == 6
+    assert lib.ek_tape_simplify(F32) == 0
+    # only the leaf and the root survive, joined by one edge whose weight is an unevaluated product chain
+    assert lib.ek_tape_node_count(F32) == 2
+    plan = ek.debug_plan()
+    assert plan.count("MULNZ_F32") + plan.count("FMANZ") >= 4, plan
+    roots = (ctypes.c_uint32 * 1)(d)
+    gv = lib.ek_tape_graphviz(F32, 1, roots)
+    from enoki_b200 import _lib
+    text = _lib.take_string(gv)
+    assert text.count("->") == 1
+    lib.ek_tape_dec_ref_ext(F32, d)
+    lib.ek_tape_dec_ref_ext(F32, leaf)
+    assert lib.ek_tape_node_count(F32) == 0
