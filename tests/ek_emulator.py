@@ -193,6 +193,8 @@ class Emulator:
                 staged[unit] = self._u(a)
             elif es == 8:
                 staged[unit] = np.ascontiguousarray(a).view(np.uint64)        # unpacked by LD_64
+            elif es == 1:
+                staged[unit] = np.ascontiguousarray(a).view(np.uint8)         # unpacked by LD_U8 / LD_S8
             else:
                 raise Unsupported("staged input of element size %d" % es)
         out_type = {var: typ for var, _aw, _bytes, typ in sw["outputs"]}
@@ -369,6 +371,16 @@ class Emulator:
                 elif name == "MAD_I32": R = R * B + C
                 elif name == "MADC_I32": R = B * C + R
                 elif name == "NEG_I32": R = np.uint32(0) - R
+                elif name == "ABS_I32": R = np.where(R.view(np.int32) < 0, np.uint32(0) - R, R)
+                elif name == "MULHI_U32": R = ((R.astype(np.uint64) * B.astype(np.uint64)) >> np.uint64(32)).astype(np.uint32)
+                elif name == "MULHI_I32": R = ((R.view(np.int32).astype(np.int64) * B.view(np.int32).astype(np.int64)) >> np.int64(32)).astype(np.int32).view(np.uint32)
+                elif name in ("LD_U8", "LD_S8"):
+                    v = staged[cb & 0x3fff]
+                    R = v.astype(np.uint32) if name == "LD_U8" else v.view(np.int8).astype(np.int32).view(np.uint32)
+                elif name == "ST_8":
+                    var = var_of_uniform(imm)
+                    self.vars[var] = (R & 0xff).astype(np.uint8).view(np.bool_) if out_type.get(var) == T_BOOL else (R & 0xff).astype(np.uint8)
+                    return
                 elif name == "NOT_32": R = ~R
                 elif name == "AND_32": R = R & B
                 elif name == "OR_32": R = R | B

@@ -271,3 +271,94 @@ def test_histogram_programs_on_the_emulator(ek, oracle, P, n_bins, n):
         assert "SCATTER_ADD_I32_SMEM" in plan and "SMEM_FLUSH_ADD_I32" in plan
     else:
         assert "SCATTER_ADD_I32 " in plan and "SMEM_ZERO" not in plan
+
+
+# ------------------------------------------------------------------ signed integers, masks, conversions
+def _build_int(EK, rng, n, n_nodes, data):
+    M = fuzz.Mirror
+    I, U, F, B = EK.Int32, EK.UInt32, EK.Float32, EK.Mask
+    il = [M(I.copy(a), a) for a in data["i32"]]
+    ul = [M(U.copy(a), a) for a in data["u32"]]
+    fl = [M(F.copy(a), a) for a in data["f32"]]
+    ml = []
+    for _ in range(n_nodes):
+        kind = rng.integers(0, 14)
+        a, b = (il[rng.integers(len(il))] for _ in range(2))
+        u, v = (ul[rng.integers(len(ul))] for _ in range(2))
+        f, g = (fl[rng.integers(len(fl))] for _ in range(2))
+        with np.errstate(all="ignore"):
+            if kind == 0: il.append(M(a.e + b.e * I(3), a.n + b.n * np.int32(3)))
+            elif kind == 1: il.append(M(-a.e - b.e, -a.n - b.n))
+            elif kind == 2: il.append(M(EK.min_(a.e, b.e) ^ EK.max_(a.e, b.e), np.minimum(a.n, b.n) ^ np.maximum(a.n, b.n)))
+            elif kind == 3:
+                s = int(rng.integers(1, 31))
+                il.append(M(a.e >> I(s), a.n >> np.int32(s)))                       # arithmetic shift
+            elif kind == 4: il.append(M(abs(a.e), np.abs(a.n)))
+            elif kind == 5: ml.append(M(a.e < b.e, a.n < b.n))
+            elif kind == 6: ml.append(M(u.e >= v.e, u.n >= v.n))
+            elif kind == 7: ml.append(M(f.e <= g.e, f.n <= g.n))
+            elif kind == 8 and len(ml) >= 2:
+                p, q = (ml[rng.integers(len(ml))] for _ in range(2))
+                ml.append(M((p.e & q.e) | ~p.e, (p.n & q.n) | ~p.n))
+            elif kind == 9 and ml:
+                p = ml[rng.integers(len(ml))]
+                il.append(M(EK.select(p.e, a.e, b.e), np.where(p.n, a.n, b.n)))
+                fl.append(M(EK.select(p.e, f.e, g.e), np.where(p.n, f.n, g.n)))
+            elif kind == 10: fl.append(M(F(a.e), a.n.astype(np.float32)))
+            elif kind == 11:
+                x = EK.max_(EK.min_(f.e, F(3.0e4)), F(-3.0e4))
+                xn = np.maximum(np.minimum(np.where(np.isnan(f.n), np.float32(3.0e4), f.n), np.float32(3.0e4)), np.float32(-3.0e4))
+                il.append(M(I(x), np.trunc(xn).astype(np.int32)))
+            elif kind == 12: ul.append(M(U(a.e) + u.e, a.n.view(np.uint32) + u.n))
+            elif kind == 13: ul.append(M(EK.mulhi(u.e, v.e), ((u.n.astype(np.uint64) * v.n.astype(np.uint64)) >> np.uint64(32)).astype(np.uint32)))
+    return il, ul, fl, ml
+
+
+def _case_int(ek, oracle, P, seed):
+    rng = np.random.default_rng(12000 + seed)
+    n = int(rng.choice([1, 65, 1000, 4097]))
+    data = {"i32": [rng.integers(-2 ** 31, 2 ** 31, n, dtype=np.int64).astype(np.int32) for _ in range(2)] + [np.array([rng.integers(-50, 50)], np.int32)],
+            "u32": [rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) for _ in range(2)],
+            "f32": [rng.uniform(-1e5, 1e5, n).astype(np.float32), np.array([rng.uniform(-2, 2)], np.float32)]}
+    table = {}
+
+    class EK:
+        Float32 = _Factory(ek.Float32, table, 0x7f0000000000)
+        UInt32 = _Factory(ek.UInt32, table, 0x7a0000000000)
+        Int32 = _Factory(ek.Int32, table, 0x760000000000)
+        Mask = ek.Mask
+        max_, min_, select, mulhi = ek.max_, ek.min_, ek.select, ek.mulhi
+
+    il, ul, fl, ml = _build_int(EK, rng, n, int(rng.integers(8, 36)), data)
+    pick = lambda lst, k: [lst[j] for j in rng.choice(len(lst), size=min(k, len(lst)), replace=False)] if lst else []
+    keep = pick(il, 3) + pick(ul, 2) + pick(fl, 2) + pick(ml, 2)
+    cnt = ek.hsum(il[-1].e)
+    del il, ul, fl, ml
+    emu = Emulator(oracle, table)
+    try:
+        emu.run(ek.debug_program())
+    except Unsupported as e:
+        return f"emulator: {e}"
+    for m in keep:
+        if m.e.index not in emu.vars:
+            raise AssertionError(f"variable {m.e.index} was not produced by any sweep")
+        got = emu.vars[m.e.index]; want = np.broadcast_to(m.n, got.shape)
+        if got.dtype == np.bool_:
+            assert (got == want).all(), (seed, n, "mask")
+        else:
+            same = np.ascontiguousarray(got).view(np.uint32) == np.ascontiguousarray(want.astype(got.dtype)).view(np.uint32)
+            if got.dtype.kind == "f":
+                same |= np.isnan(got) & np.isnan(want)
+            assert same.all(), (seed, n, got.dtype, got[~same][:3], want[~same][:3])
+    return None
+
+
+@pytest.mark.parametrize("seed", range(100))
+def test_random_integer_and_mask_dags_on_the_emulator(ek, oracle, P, seed):
+    import gc
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    assert ek.debug_plan() == "", "unevaluated variables of an earlier test are still alive"
+    reason = _case_int(ek, oracle, P, seed)
+    gc.collect()
+    if reason:
+        pytest.skip(reason)
