@@ -362,3 +362,37 @@ def test_random_integer_and_mask_dags_on_the_emulator(ek, oracle, P, seed):
     gc.collect()
     if reason:
         pytest.skip(reason)
+
+
+def _case_phases(ek, oracle, P):
+    """Reductions feed later phases of the same evaluation: y = x / hsum(x), z = (x - hmin(x)) * (hmax(x) - x)."""
+    rng = np.random.default_rng(3)
+    n = 3001
+    table = {}
+    F = _Factory(ek.Float32, table, 0x7f0000000000); U = _Factory(ek.UInt32, table, 0x7a0000000000)
+    xn = rng.uniform(0.5, 2.0, n).astype(np.float32); un = rng.integers(0, 1000, n, dtype=np.uint64).astype(np.uint32)
+    x = F.copy(xn); u = U.copy(un)
+    y = x / ek.hsum(x)
+    z = (x - ek.hmin(x)) * (ek.hmax(x) - x)
+    c = u + ek.hmax(u) - ek.hmin(u)
+    p = ek.hprod(F.copy(np.linspace(0.9, 1.1, 9, dtype=np.float32)))
+    prog = ek.debug_program()
+    phases = sorted({sw["phase"] for sw in prog["sweeps"]})
+    emu = Emulator(oracle, table)
+    emu.run(prog)
+    s = np.float32(xn.astype(np.float64).sum())
+    assert np.allclose(emu.vars[y.index], xn / s, rtol=1e-6)
+    zn = (xn - xn.min()) * (xn.max() - xn)
+    assert (emu.vars[z.index].view(np.uint32) == zn.view(np.uint32)).all()
+    assert (emu.vars[c.index].view(np.uint32) == un + un.max() - un.min()).all()
+    assert abs(float(emu.vars[p.index][0]) - float(np.prod(np.linspace(0.9, 1.1, 9, dtype=np.float32).astype(np.float64)))) < 1e-6
+    return phases
+
+
+def test_reduction_phases_on_the_emulator(ek, oracle, P):
+    import gc
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    assert ek.debug_plan() == ""
+    phases = _case_phases(ek, oracle, P)
+    gc.collect()
+    assert phases == [0, 1]
