@@ -234,20 +234,21 @@ __global__ void __launch_bounds__(32) part_scatter(const uint64_t *keys, uint32_
     for (uint32_t k = threadIdx.x; k < K; k += 32u) { sk[k] = uniq[k]; pos[k] = hist[(size_t) blockIdx.x * K + k]; }
     __syncwarp();
     const uint32_t base = blockIdx.x * PART_CHUNK, lane = threadIdx.x;
+    /* every warp-level primitive below is executed by all 32 lanes with the full mask (lanes past the end of the array
+       form a group of their own with the bucket id ~0): no lane ever waits at a barrier with a different mask */
     for (uint32_t j = 0; j < PART_CHUNK; j += 32u) {
         const uint32_t i = base + j + lane;
         const bool active = i < n;
-        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        const uint32_t b = active ? part_bucket(sk, K, keys[i]) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
+        const uint32_t first = active ? pos[b] : 0u;
+        __syncwarp();                                   /* everybody has read the running positions */
         if (active) {
-            const uint32_t b = part_bucket(sk, K, keys[i]);
-            const unsigned peers = __match_any_sync(amask, b);
-            const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
-            const uint32_t first = pos[b];
             dst[b][first + rank] = i;
-            __syncwarp(amask);
             if (rank == 0) pos[b] = first + (uint32_t) __popc(peers);
         }
-        __syncwarp();
+        __syncwarp();                                   /* ... and sees the updated ones in the next step */
     }
 }
 } // namespace
@@ -287,10 +288,13 @@ int ek_compress(ek_type type, size_t n, const void *data, const uint8_t *mask, v
    values fall back to a host-side stable sort. */
 int ek_partition(size_t n, const void **ptrs, void ***unique_out, uint32_t **counts_out, uint32_t ***perm_out) {
     /* Round-1 status: written and compiled, NOT yet verified on hardware -- the first two GPU runs of
-       tests/cpp/call_check ended with the loss of the GPU box before any output came back, and the cause was not
-       isolated.  Until it is, the entry point keeps its documented round-1 behaviour (an error) unless
-       EK_ENABLE_PARTITION=1 is set; tests/test_gpu_eval.py::test_partition and tests/cpp/call_check are the
-       checks to run first in round 2. */
+       tests/cpp/call_check ended with the loss of the GPU box after ~2 minutes (a hung kernel).  The likely cause was
+       found by inspection afterwards and fixed: part_scatter synchronised the lanes of a ragged last step with
+       __syncwarp(active-mask) inside a branch while the inactive lanes waited at __syncwarp(full mask) -- undefined
+       behaviour that only shows when n is not a multiple of 32 (it was 100003); every warp primitive there now runs
+       on all 32 lanes with the full mask.  No GPU time was left to confirm it, so the entry point keeps its
+       documented round-1 behaviour (an error) unless EK_ENABLE_PARTITION=1 is set; tests/test_gpu_eval.py::test_partition
+       and tests/cpp/call_check are the checks to run first in round 2 (under a short timeout). */
     if (getenv("EK_ENABLE_PARTITION") == nullptr) {
         ek_set_error("ek_partition(): not enabled (unverified in this round; set EK_ENABLE_PARTITION=1 to try it, SURVEY.md 8f row 1)");
         return -1;
