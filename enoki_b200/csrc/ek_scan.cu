@@ -168,20 +168,19 @@ __global__ void __launch_bounds__(256) part_discover(const uint64_t *keys, uint3
         const uint64_t k = keys[i];
         const unsigned peers = __match_any_sync(amask, k);
         if (lane != (uint32_t) (__ffs(peers) - 1)) continue;
+        /* open addressing with ONE compare-and-swap per probe and no waiting: a slot holds key + 1 (0 = empty; ~0 is
+           not a pointer value), so claiming a slot and publishing its key are the same atomic operation */
         uint32_t h = part_hash(k);
+        const uint32_t c = (uint32_t) __popc(peers);
         for (uint32_t probe = 0; probe < PART_SLOTS; ++probe, h = (h + 1) & (PART_SLOTS - 1)) {
-            uint32_t was = atomicCAS(&tab->used[h], 0u, 1u);
-            if (was == 0u) {                                   /* claimed an empty slot */
-                atomicExch(&tab->key[h], (unsigned long long) k);
-                __threadfence();
-                atomicExch(&tab->used[h], 2u);
+            const unsigned long long prev = atomicCAS(&tab->key[h], 0ull, (unsigned long long) k + 1ull);
+            if (prev == 0ull) {                                /* first sighting of this value */
+                tab->used[h] = 1u;
                 if (atomicAdd(&tab->n_used, 1u) >= PART_MAX_UNIQUE) tab->overflow = 1u;
-                atomicAdd(&tab->count[h], (uint32_t) __popc(peers));
+                atomicAdd(&tab->count[h], c);
                 break;
             }
-            while (was != 2u) was = atomicAdd(&tab->used[h], 0u);   /* another thread is publishing the key */
-            __threadfence();
-            if (atomicAdd(&tab->key[h], 0ull) == (unsigned long long) k) { atomicAdd(&tab->count[h], (uint32_t) __popc(peers)); break; }
+            if (prev == (unsigned long long) k + 1ull) { atomicAdd(&tab->count[h], c); break; }
             if (tab->overflow) break;
         }
     }
@@ -318,7 +317,7 @@ int ek_partition(size_t n, const void **ptrs, void ***unique_out, uint32_t **cou
     bool overflow = tab_h->overflow != 0;
     if (!overflow) {
         std::vector<std::pair<uint64_t, uint32_t>> found;
-        for (uint32_t i = 0; i < PART_SLOTS; ++i) if (tab_h->used[i]) found.emplace_back(tab_h->key[i], tab_h->count[i]);
+        for (uint32_t i = 0; i < PART_SLOTS; ++i) if (tab_h->key[i]) found.emplace_back(tab_h->key[i] - 1ull, tab_h->count[i]);
         std::sort(found.begin(), found.end());
         for (auto &f : found) { uniq.push_back(f.first); cnts.push_back(f.second); }
     }
