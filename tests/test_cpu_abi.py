@@ -204,3 +204,30 @@ def test_simplify_graph_structure_cpu(ek):
     lib.ek_tape_dec_ref_ext(F32, d)
     lib.ek_tape_dec_ref_ext(F32, leaf)
     assert lib.ek_tape_node_count(F32) == 0
+
+
+def test_cpp_header_shim_records_the_same_programs(ek):
+    """The C++ drop-in header (include/enoki/cuda.h under the reference's router / array_math.h) must record what the
+    Python mirror records: tests/cpp/shim_plan prints the planner's listing for expressions written as user C++ code."""
+    import subprocess
+    binp = os.path.join(ROOT, "tests", "cpp", "shim_plan")
+    if not os.path.exists(binp):
+        pytest.skip("tests/cpp/shim_plan not built (needs the reference headers at build time)")
+    out = subprocess.run([binp], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    sections = dict((s.split("\n", 1)[0].strip(), s.split("\n", 1)[1]) for s in out.stdout.split("== ")[1:])
+    # C2 through the Python mirror
+    n = 1 << 20
+    x = [_fake(ek, n, k) for k in range(4)]
+    t = ek.fmadd(x[0], x[1], x[2])
+    o = ek.fmadd(ek.sin(ek.fmadd(x[3], ek.exp(-(t * t)), x[0])), x[1], ek.sqrt(abs(t)))
+    del t
+    want = ek.debug_plan()
+    del o
+    strip = lambda s: "\n".join(re.sub(r"imm=0x[0-9a-f]+", "", l).rstrip() for l in s.strip().splitlines())
+    assert strip(sections["c2"]) == strip(want)
+    # reduction feeding a later phase, conversions, select: structure of the second listing
+    ph = sections["phases"]
+    sweeps = [l for l in ph.splitlines() if l.startswith("sweep")]
+    assert len(sweeps) == 2 and "phase=0" in sweeps[0] and "phase=1" in sweeps[1] and "scalars=1" in sweeps[1]
+    assert "RFIN" in ph and "CVT_F32_U32" in ph and "SEL_T_32" in ph
