@@ -116,6 +116,7 @@ SIGNATURES = {
     "ek_debug_plan": (c_vp, []),
     "ek_debug_program": (c_vp, []),
     "ek_debug_discard_side_effects": (None, []),
+    "ek_debug_tape_edge_weight": (c_u32, [c_int, c_u32, c_u32]),
 }
 
 _lib = None

@@ -1077,4 +1077,15 @@ void ek_tape_clear(ek_type t) {
     T->sg_index = nullptr;
 }
 
+/* host-only test aid: evaluator handle of the weight of edge src -> dst (0 if there is no such ordinary edge); lets the
+   CPU test-suite execute the fused weight products simplify_graph() records (tests/ek_emulator.py) */
+EK_API uint32_t ek_debug_tape_edge_weight(ek_type t, uint32_t src, uint32_t dst) {
+    Tape *T = tape_of(t); if (!T) return 0;
+    auto it = T->nodes.find(dst);
+    if (it == T->nodes.end()) return 0;
+    for (const TEdge &e : it->second.edges)
+        if (e.source == src && !e.special) return e.weight;
+    return 0;
+}
+
 } /* extern "C" */

@@ -348,6 +348,9 @@ class Emulator:
                 elif name == "DIVR_F32": R = self._u(f(B) / f(R))
                 elif name == "FMA_F32": R = self._fma(R, B, C)
                 elif name == "FMAC_F32": R = self._fma(B, C, R)
+                elif name == "MULNZ_F32": R = np.where((f(R) == 0) | (f(B) == 0), np.uint32(0), self._u(f(R) * f(B)))
+                elif name == "FMANZ_F32": R = np.where((f(R) == 0) | (f(B) == 0), C, self._fma(R, B, C))
+                elif name == "FMANZC_F32": R = np.where((f(B) == 0) | (f(C) == 0), R, self._fma(B, C, R))
                 elif name in ("MIN_F32", "MAX_F32"): R = self._minmax(name == "MAX_F32", R, B)
                 elif name in ("MINR_F32", "MAXR_F32"): R = self._minmax(name == "MAXR_F32", B, R)
                 elif name == "ABS_F32": R = R & np.uint32(0x7fffffff)

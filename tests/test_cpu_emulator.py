@@ -396,3 +396,45 @@ def test_reduction_phases_on_the_emulator(ek, oracle, P):
     phases = _case_phases(ek, oracle, P)
     gc.collect()
     assert phases == [0, 1]
+
+
+def _case_simplified_weights(ek, oracle, P):
+    """simplify_graph() (autodiff.cpp:990-1074) on a chain with a diamond: the surviving leaf -> root edge carries
+    w0*w1*w2*(w4 + w3*w5) as a traced mul_nz / fma_nz expression; executed here by the emulator."""
+    import ctypes
+    lib = ek.lib(); F32 = ek.EK_FLOAT32
+    n = 257
+    rng = np.random.default_rng(11)
+    table = {}
+    F = _Factory(ek.Float32, table, 0x7f0000000000)
+    wn = [rng.uniform(0.5, 1.5, n).astype(np.float32) for _ in range(6)]
+    wn[1][::7] = 0.0                             # exact zeros exercise the *_nz guards
+    ws = [F.copy(a) for a in wn]
+
+    def node(label, srcs, wl):
+        idx = (ctypes.c_uint32 * len(srcs))(*srcs); wh = (ctypes.c_uint32 * len(wl))(*[w.index for w in wl])
+        h = lib.ek_tape_append(F32, label, n, len(srcs), idx, wh); assert h
+        return h
+    leaf = lib.ek_tape_append_leaf(F32, n)
+    a = node(b"a", [leaf], [ws[0]]); b = node(b"b", [a], [ws[1]]); c = node(b"c", [b], [ws[2]])
+    c2 = node(b"c2", [c], [ws[3]]); d = node(b"d", [c, c2], [ws[4], ws[5]])
+    for h in (a, b, c, c2):
+        lib.ek_tape_dec_ref_ext(F32, h)
+    assert lib.ek_tape_simplify(F32) == 0 and lib.ek_tape_node_count(F32) == 2
+    w = lib.ek_debug_tape_edge_weight(F32, leaf, d)
+    assert w != 0
+    emu = Emulator(oracle, table)
+    emu.run(ek.debug_program())
+    got = emu.vars[w].astype(np.float64)
+    want = (wn[0].astype(np.float64) * wn[1] * wn[2]) * (wn[4].astype(np.float64) + wn[3].astype(np.float64) * wn[5])
+    assert np.allclose(got, want, rtol=2e-6, atol=0) and (got[::7] == 0).all()
+    lib.ek_tape_dec_ref_ext(F32, d); lib.ek_tape_dec_ref_ext(F32, leaf)
+    assert lib.ek_tape_node_count(F32) == 0
+
+
+def test_simplified_edge_weights_on_the_emulator(ek, oracle, P):
+    import gc
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    assert ek.debug_plan() == ""
+    _case_simplified_weights(ek, oracle, P)
+    gc.collect()
