@@ -216,6 +216,9 @@ def test_cpp_header_shim_records_the_same_programs(ek):
     out = subprocess.run([binp], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     sections = dict((s.split("\n", 1)[0].strip(), s.split("\n", 1)[1]) for s in out.stdout.split("== ")[1:])
+    import gc
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()      # scatters recorded by earlier tests
+    assert ek.debug_plan() == ""
     # C2 through the Python mirror
     n = 1 << 20
     x = [_fake(ek, n, k) for k in range(4)]
