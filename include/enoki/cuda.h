@@ -382,23 +382,24 @@ struct CUDAArray : ArrayBase<value_t<Value>, CUDAArray<Value>> {
     /// Round 1: ek_partition is unverified and answers with an error unless EK_ENABLE_PARTITION=1 (see ek_scan.cu).
     template <typename T = Value, enable_if_t<std::is_pointer_v<T> || std::is_same_v<T, uintptr_t>> = 0>
     std::vector<std::pair<Value, CUDAArray<uint32_t>>> partition_() const {
-        if (!m_cached_partition) {
-            eval();
-            void **unique = nullptr;
-            uint32_t *counts = nullptr;
-            uint32_t **perm = nullptr;
-            cuda_partition(size(), (const void **) data(), &unique, &counts, &perm);
-            uint32_t num_unique = counts[0];
-            m_cached_partition = new std::vector<std::pair<Value, CUDAArray<uint32_t>>>();
-            m_cached_partition->reserve(num_unique);
-            for (uint32_t i = 0; i < num_unique; ++i)
-                m_cached_partition->emplace_back((Value) unique[i],
-                    CUDAArray<uint32_t>::from_index_(cuda_var_register(EnokiType::UInt32, counts[i + 1], perm[i], true)));
-            cuda_host_free(unique);
-            cuda_host_free(counts);
-            free(perm);
+        using Groups = std::vector<std::pair<Value, CUDAArray<uint32_t>>>;
+        if (m_cached_partition)
+            return *m_cached_partition;
+        eval();
+        /* ek_partition hands back: pinned-host instance pointers and counts (counts[0] = number of groups), and a
+           malloc'd array of device index lists, one per group (ownership as horiz.cu:83-121) */
+        void **instances = nullptr; uint32_t *sizes = nullptr; uint32_t **lists = nullptr;
+        cuda_partition(size(), (const void **) data(), &instances, &sizes, &lists);
+        Groups *groups = new Groups();
+        const uint32_t n_groups = sizes[0];
+        groups->reserve(n_groups);
+        for (uint32_t g = 0; g < n_groups; ++g) {
+            uint32_t handle = cuda_var_register(EnokiType::UInt32, sizes[g + 1], lists[g], /* dealloc = */ true);
+            groups->emplace_back((Value) instances[g], CUDAArray<uint32_t>::from_index_(handle));
         }
-        return *m_cached_partition;
+        cuda_host_free(instances); cuda_host_free(sizes); free(lists);
+        m_cached_partition = groups;
+        return *groups;
     }
 
     Index index_() const { return m_index; }
