@@ -69,7 +69,13 @@ struct Assembled {
     int release_at = -1;                        /* body index of that instruction */
     uint64_t bytes_in = 0, bytes_out = 0;
     struct DescFix { uint32_t argw; uint32_t count_limit; };
-    std::vector<uint32_t> copies_fix;           /* argw index of Desc.copies (set from config) */
+    /* shared-memory 'extra' region: staged gather tables and privatised scatter_add bins; the offsets / copy counts
+       written into the descriptors at assembly time are the general kernels' layout -- the fast kernel re-lays the
+       region out for its block size (layout_extra) */
+    struct ExtraItem { uint32_t di; uint32_t count; uint8_t kind; };   /* kind 0 table, 1 float bins, 2 integer bins */
+    std::vector<ExtraItem> extra_items;
+    bool fast_ok = false;                       /* every instruction has a fast-kernel form (lower_fast) */
+    uint32_t fast_len = 0;                      /* number of lowered instructions */
     std::string error;
     bool resource_error = false;     /* a limit was hit: the caller may split the group and retry */
 };
@@ -637,6 +643,7 @@ struct Assembler {
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(1); out.argw.push_back(pa);
                     out.extra_bytes += (count * 4 + 15) & ~15u;
+                    out.extra_items.push_back({ di, count, 0 });
                     EkInstr li = mk(DOP_SMEM_LOAD_TABLE, di); set_mark(li, 1);
                     out.init.push_back(li);
                     in = mk(DOP_GATHER_32_SMEM, di); set_mark(in, 1);
@@ -683,6 +690,7 @@ struct Assembler {
                     uint32_t di = (uint32_t) out.argw.size();
                     out.argw.push_back(out.extra_bytes); out.argw.push_back(count); out.argw.push_back(copies); out.argw.push_back(pa);
                     out.extra_bytes += (count * copies * 4 + 15) & ~15u;
+                    out.extra_items.push_back({ di, count, (uint8_t) (dop == DOP_SCATTER_ADD_F32 ? 1 : 2) });
                     EkInstr zi = mk(DOP_SMEM_ZERO, di); set_mark(zi, 1); out.init.push_back(zi);
                     EkInstr fl = mk(dop == DOP_SCATTER_ADD_F32 ? DOP_SMEM_FLUSH_ADD_F32 : DOP_SMEM_FLUSH_ADD_I32, di); set_mark(fl, 1);
                     out.fini.push_back(fl);
@@ -1092,21 +1100,165 @@ struct Planner {
     }
 };
 
+/* Layout of the 'extra' shared-memory region for one configuration.  General kernels: the assembly-time layout.
+   Fast kernel (V = 16): scatter_add bins of up to 32 KB get ONE PRIVATE COPY PER THREAD (integer as well as float bins:
+   plain LDS / add / STS, bank = thread id whatever the bin -- no shared-memory atomics); larger targets keep the
+   [bin][copy] layout with up to 32 copies updated atomically.  Returns the size; writes offsets / copy counts into
+   `argw` when it is given. */
+uint32_t fast_copies(uint32_t count, uint32_t T) {
+    return (uint64_t) count * T * 4u <= 32768u ? T : std::max(1u, std::min(32u, 4096u / count));
+}
+size_t layout_extra(const Assembled &a, const Config &cfg, uint32_t *argw) {
+    if (cfg.V != 16) return a.extra_bytes;
+    uint32_t off = 0;
+    for (const Assembled::ExtraItem &it : a.extra_items) {
+        uint32_t copies = it.kind == 0 ? 1u : fast_copies(it.count, cfg.T);
+        if (argw) { argw[it.di] = off; argw[it.di + 2] = copies; }
+        off += (it.count * copies * 4u + 15u) & ~15u;
+    }
+    return off;
+}
+
 size_t smem_layout(const Assembled &a, Config &cfg, size_t n_uni) {
     size_t off = n_uni * 16;                        /* every uniform word is replicated 4x */
     cfg.off_bar = (uint32_t) off; off += 8 * 8 + 33 * 8;
     off = (off + 15) & ~(size_t) 15;
     size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
-    cfg.prog_in_smem = n_prog * 16 <= 24 * 1024;
+    cfg.prog_in_smem = cfg.V != 16 && n_prog * 16 <= 24 * 1024;
     cfg.off_prog = (uint32_t) off;
     if (cfg.prog_in_smem) off += n_prog * 16;
-    cfg.off_extra = (uint32_t) off; off += a.extra_bytes;
+    cfg.off_extra = (uint32_t) off; off += layout_extra(a, cfg, nullptr);
     off = (off + 1023) & ~(size_t) 1023;
     cfg.off_slots = (uint32_t) off;
     size_t slot_bytes = (size_t) cfg.T * cfg.V * 4;
     off += slot_bytes * (a.n_tmp + (size_t) cfg.stages * a.n_in_units);
     cfg.smem = off;
     return off;
+}
+
+/* ---- lowering for the 32-bit fast kernel (ek_sweep_fast.cu; format: ek_isa.h "lowered instruction format") ---- */
+int fop_of(int dop) {
+    switch (dop) {
+        case DOP_NOP: return FOP_NOP;
+#define X(n) case DOP_##n: return FOP_##n;
+        EK_FOPS2(X)
+        X(FMA_F32) X(FMAC_F32) X(MAD_I32) X(MADC_I32) X(FMANZ_F32) X(FMANZC_F32) X(SEL_M_32) X(SEL_T_32) X(SEL_F_32)
+        X(ABS_F32) X(NEG_F32) X(SQRT_F32) X(RCP_F32) X(RSQRT_F32) X(EXP_F32) X(LOG_F32) X(SIN_F32) X(COS_F32)
+        X(FLOOR_F32) X(CEIL_F32) X(ROUND_F32) X(TRUNC_F32) X(ABS_I32) X(NEG_I32) X(NOT_32) X(NOT_B) X(NEZ_32)
+        X(CVT_F32_I32) X(CVT_F32_U32) X(CVT_I32_F32) X(CVT_U32_F32)
+        X(INDEX) X(LD_U8) X(LD_S8) X(LDG_32) X(ST_32) X(ST_8)
+        X(GATHER_32) X(GATHER_32_SMEM) X(SCATTER_32) X(SCATTER_ADD_F32) X(SCATTER_ADD_I32)
+        X(SCATTER_ADD_F32_SMEM) X(SCATTER_ADD_I32_SMEM) X(RACC)
+        EK_FOPS0(X)
+#undef X
+        case DOP_LOAD_32: return FOP_LOAD;
+        default: return -1;
+    }
+}
+bool fop_has_u_twin(int fop) {
+    switch (fop) {
+#define X(n) case FOP_##n:
+        EK_FOPS2(X)
+#undef X
+            return true;
+        default: return false;
+    }
+}
+
+/* `in` = assembled instructions whose operand codes are still symbolic (uniform index | 0x8000, staged unit | 0x4000,
+   temporary slot); cfg == nullptr: count / check only.  Appends to `out`; false = not expressible. */
+bool lower_fast(const std::vector<EkInstr> &in, const Assembled &a, const Config *cfg, std::vector<EkInstr> &out) {
+    const uint32_t slot_bytes = cfg ? cfg->T * 16u * 4u : 0u;
+    auto is_uni = [](uint16_t c) { return c != EK_OPND_NONE && (c & EK_OPND_UNI) != 0; };
+    /* per-thread operand -> absolute byte offset >> 4; uniform operand -> pool word index */
+    auto enc = [&](uint16_t c) -> uint16_t {
+        if (c == EK_OPND_NONE) return 0;
+        if (c & EK_OPND_UNI) return (uint16_t) (c & 0x7fffu);
+        if (!cfg) return 0;
+        uint32_t off = (c & EK_OPND_STAGED) ? cfg->off_slots + (a.n_tmp + (c & 0x3fffu)) * slot_bytes
+                                            : cfg->off_slots + (uint32_t) c * slot_bytes;
+        return (uint16_t) (off >> 4);
+    };
+    auto emit = [&](uint32_t fop, uint32_t fl, uint16_t b, uint16_t c, uint16_t dst, uint16_t aux, uint32_t imm) {
+        EkInstr o;
+        o.op = (uint16_t) fop; o.flags = (uint16_t) fl; o.dst = b; o.b = c; o.c = dst; o.a = aux; o.imm = imm;
+        /* (EkInstr field order = word layout x = op | flags << 16, y = dst | b << 16, z = c | a << 16: the lowered
+           format reads y = b | c << 16, z = dst | aux << 16 -- hence the shuffled assignment above) */
+        out.push_back(o);
+    };
+    for (const EkInstr &i : in) {
+        if (i.flags & (EKF_R64 | EKF_B64 | EKF_C64 | EKF_A64 | EKF_REL)) return false;
+        /* 1. accumulator load and input modifiers become instructions of their own */
+        if (i.flags & EKF_HAS_A) {
+            if (is_uni(i.a)) emit(FOP_LOADU, 0, enc(i.a), 0, 0, 0, 0);
+            else emit(FOP_LOAD, 0, enc(i.a), 0, 0, 0, 0);
+        }
+        if (i.flags & EKF_ABS_A) emit(FOP_ABS_F32, 0, 0, 0, 0, 0, 0);
+        if (i.flags & EKF_NEG_A) emit(FOP_NEG_F32, 0, 0, 0, 0, 0, 0);
+        /* 2. the operation */
+        int fop = fop_of(i.op);
+        if (fop < 0) return false;
+        uint32_t fl = 0;
+        uint16_t b = 0, c = 0, dst = 0, aux = 0;
+        const bool hb = (i.flags & EKF_HAS_B) != 0, hc = (i.flags & EKF_HAS_C) != 0;
+        const bool ub = hb && is_uni(i.b), uc = hc && is_uni(i.c);
+        if (hb) b = enc(i.b);
+        if (hc) c = enc(i.c);
+        switch (i.op) {
+            case DOP_LOAD_32:                                     /* R = B */
+                if (!hb) return false;
+                fop = ub ? FOP_LOADU : FOP_LOAD;
+                break;
+            case DOP_LD_U8: case DOP_LD_S8:                       /* raw staged code in b, no EKF_HAS_B */
+                b = enc(i.b);
+                break;
+            case DOP_GATHER_32: case DOP_GATHER_32_SMEM:          /* mask = B */
+                if (!hb) return false;
+                fl |= ub ? FF_MU : FF_B;
+                break;
+            case DOP_SCATTER_32: case DOP_SCATTER_ADD_F32: case DOP_SCATTER_ADD_I32:
+            case DOP_SCATTER_ADD_F32_SMEM: case DOP_SCATTER_ADD_I32_SMEM:     /* value = B, mask = C */
+                if (!hb || !hc) return false;
+                fl |= ub ? FF_VU : FF_B;
+                fl |= uc ? FF_MU : FF_C;
+                break;
+            case DOP_FMA_F32:
+                if (ub && !uc) { fop = FOP_FMA_F32_UB; fl |= FF_C; }
+                else if (uc && !ub) { fop = FOP_FMA_F32_UC; fl |= FF_B; }
+                else if (ub && uc) { fop = FOP_FMA_F32_UB; fl |= FF_CU; }
+                else fl |= FF_B | FF_C;
+                break;
+            case DOP_FMAC_F32:                                    /* B * C + R (commutative in B, C) */
+                if (ub && !uc) { fop = FOP_FMAC_F32_UB; fl |= FF_C; }
+                else if (uc && !ub) { fop = FOP_FMAC_F32_UB; std::swap(b, c); fl |= FF_C; }
+                else if (ub && uc) { fop = FOP_FMAC_F32_UB; fl |= FF_CU; }
+                else fl |= FF_B | FF_C;
+                break;
+            case DOP_RFIN:                                        /* b = slot of the partials, dst = pool index of the pointer */
+                if (!hb || ub) return false;
+                dst = i.dst;
+                break;
+            default:
+                if (hb && ub && !hc && fop_has_u_twin(fop)) fop += 1;          /* X_U = X + 1 */
+                else {
+                    if (hb) fl |= ub ? FF_BU : FF_B;
+                    if (hc) fl |= uc ? FF_CU : FF_C;
+                }
+                break;
+        }
+        /* 3. post actions */
+        if (i.flags & EKF_ST) { fl |= FF_ST; dst = enc(i.dst); }
+        if (i.flags & EKF_STG) fl |= FF_STG;
+        if ((i.flags & EKF_RACC) || i.op == DOP_RACC) {
+            if (i.flags & EKF_ST) return false;
+            fl |= FF_RACC; dst = enc(i.dst);
+            aux = (uint16_t) (i.op == DOP_RACC ? (i.imm & 0xffffu) : i.a);
+            if (((aux >> 8) & 0xffu) > EK_RC_U32) return false;
+        }
+        if (i.op == DOP_NOP && !fl) continue;                    /* (a bare carrier of a load / modifier) */
+        emit((uint32_t) fop, fl, b, c, dst, aux, i.imm);
+    }
+    return true;
 }
 
 bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &cfg, std::string &err) {
@@ -1118,17 +1270,18 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
         /* measured on B200 (tools/cfgsweep.sh): single-buffered staging with more resident CTAs beats
            double buffering -- the other CTAs of the SM hide the TMA latency and 16 warps hide the
            interpreter's dependent-issue latency */
-        { 16, 256, 1, 2 }, { 16, 128, 1, 4 }, { 16, 128, 1, 3 }, { 16, 128, 2, 2 }, { 16, 128, 1, 2 },
-        { 16, 256, 2, 1 }, { 16, 128, 1, 1 },                               /* 32-bit-only programs */
+        { 16, 256, 1, 2 }, { 16, 128, 1, 4 }, { 16, 128, 1, 3 }, { 16, 128, 1, 2 }, { 16, 256, 1, 1 }, { 16, 128, 1, 1 },
+                                                      /* 32-bit-only programs: the fast kernel (single TMA stage) */
         { 8, 256, 1, 4 }, { 8, 256, 1, 3 }, { 8, 256, 2, 2 }, { 8, 256, 1, 2 }, { 8, 256, 2, 1 }, { 8, 256, 1, 1 },
         { 8, 128, 1, 2 }, { 8, 128, 2, 1 }, { 8, 128, 1, 1 },
         { 4, 128, 2, 1 }, { 4, 64, 2, 1 }, { 4, 32, 2, 1 } };
     size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
-    bool fast_ok = !a.has64 && !a.noncore && n_prog <= EK_INLINE_PROG;
+    (void) n_prog;
+    bool fast_ok = !a.has64 && !a.noncore && a.fast_ok && a.fast_len <= EK_INLINE_PROG;
     /* tuning aid: EK_CFG="V,T,stages,ctas_per_sm" forces a configuration for wide sweeps */
     if (const char *env = getenv("EK_CFG")) {
         int V, T, S, C;
-        if (n > 4096 && sscanf(env, "%d,%d,%d,%d", &V, &T, &S, &C) == 4 && (V != 16 || fast_ok)) {
+        if (n > 4096 && sscanf(env, "%d,%d,%d,%d", &V, &T, &S, &C) == 4 && (V != 16 || (fast_ok && S == 1 && (T == 128 || T == 256)))) {
             cfg.V = V; cfg.T = (uint32_t) T; cfg.stages = (uint32_t) S; cfg.ctas_per_sm = (uint32_t) C;
             if (smem_layout(a, cfg, n_uni) <= budget) return true;
         }
@@ -1144,7 +1297,7 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
     }
     for (const Cand &c : cands) {
         if (c.V == 16 && !fast_ok) continue;
-        cfg.V = c.V; cfg.T = c.T; cfg.stages = a.n_in_units ? c.stages : 2; cfg.ctas_per_sm = c.want_ctas;
+        cfg.V = c.V; cfg.T = c.T; cfg.stages = (a.n_in_units || c.V == 16) ? c.stages : 2; cfg.ctas_per_sm = c.want_ctas;
         size_t need = smem_layout(a, cfg, n_uni);
         if (need > budget) continue;
         if ((need + 1024) * c.want_ctas > per_sm + 1024) continue;
@@ -1161,32 +1314,52 @@ uint64_t fnv1a(const uint8_t *p, size_t n) {
     return h;
 }
 
-void lookup_program(EkContext &ctx, const Assembled &a, const EkInstr *&d_prog, const uint32_t *&d_lit) {
+/* device copies of programs / literal pools that do not fit the kernel parameters (rare: > 448 instructions or > 128
+   literal words).  Keyed on exactly what is uploaded; bounded: the cache is emptied when it reaches 256 entries (the
+   stream is synchronised first, so no launch still reads the freed buffers). */
+void lookup_program(EkContext &ctx, const Assembled &a, bool need_prog, bool need_lit, const EkInstr *&d_prog, const uint32_t *&d_lit) {
     std::vector<uint8_t> key;
     auto append = [&](const void *p, size_t n) { const uint8_t *b = (const uint8_t *) p; key.insert(key.end(), b, b + n); };
-    uint32_t hdr[3] = { (uint32_t) a.init.size(), (uint32_t) a.body.size(), (uint32_t) a.fini.size() };
+    uint32_t hdr[4] = { need_prog ? (uint32_t) a.init.size() : 0u, need_prog ? (uint32_t) a.body.size() : 0u, need_prog ? (uint32_t) a.fini.size() : 0u,
+                        need_lit ? (uint32_t) a.lits.size() : 0u };
     append(hdr, sizeof(hdr));
-    append(a.init.data(), a.init.size() * sizeof(EkInstr));
-    append(a.body.data(), a.body.size() * sizeof(EkInstr));
-    append(a.fini.data(), a.fini.size() * sizeof(EkInstr));
-    append(a.lits.data(), a.lits.size() * 4);
+    if (need_prog) {
+        append(a.init.data(), a.init.size() * sizeof(EkInstr));
+        append(a.body.data(), a.body.size() * sizeof(EkInstr));
+        append(a.fini.data(), a.fini.size() * sizeof(EkInstr));
+    }
+    if (need_lit) append(a.lits.data(), a.lits.size() * 4);
     uint64_t h = fnv1a(key.data(), key.size());
-    auto &bucket = ctx.programs[h];
-    for (auto &e : bucket) if (e.key == key) { d_prog = e.d_prog; d_lit = e.d_lit; return; }
+    {
+        auto it = ctx.programs.find(h);
+        if (it != ctx.programs.end())
+            for (auto &e : it->second) if (e.key == key) { d_prog = e.d_prog; d_lit = e.d_lit; return; }
+    }
+    size_t entries = 0;
+    for (auto &kv : ctx.programs) entries += kv.second.size();
+    if (entries >= 256) {
+        ek_cuda_check(cudaStreamSynchronize(ctx.stream));
+        for (auto &kv : ctx.programs) for (auto &e : kv.second) { if (e.d_prog) cudaFree(e.d_prog); if (e.d_lit) cudaFree(e.d_lit); }
+        ctx.programs.clear();
+    }
     EkProgramCacheEntry e;
     e.key = key;
-    size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
-    std::vector<EkInstr> all;
-    all.insert(all.end(), a.init.begin(), a.init.end());
-    all.insert(all.end(), a.body.begin(), a.body.end());
-    all.insert(all.end(), a.fini.begin(), a.fini.end());
-    ek_cuda_check(cudaMalloc(&e.d_prog, std::max<size_t>(n_prog, 1) * sizeof(EkInstr)));
-    ek_cuda_check(cudaMalloc(&e.d_lit, std::max<size_t>(a.lits.size(), 1) * 4));
-    /* synchronous copies from pageable memory: only on a cache miss */
-    if (n_prog) ek_cuda_check(cudaMemcpy(e.d_prog, all.data(), n_prog * sizeof(EkInstr), cudaMemcpyHostToDevice));
-    if (!a.lits.empty()) ek_cuda_check(cudaMemcpy(e.d_lit, a.lits.data(), a.lits.size() * 4, cudaMemcpyHostToDevice));
+    e.d_prog = nullptr; e.d_lit = nullptr;
+    if (need_prog) {
+        std::vector<EkInstr> all;
+        all.insert(all.end(), a.init.begin(), a.init.end());
+        all.insert(all.end(), a.body.begin(), a.body.end());
+        all.insert(all.end(), a.fini.begin(), a.fini.end());
+        ek_cuda_check(cudaMalloc(&e.d_prog, std::max<size_t>(all.size(), 1) * sizeof(EkInstr)));
+        /* synchronous copies from pageable memory: only on a cache miss */
+        if (!all.empty()) ek_cuda_check(cudaMemcpy(e.d_prog, all.data(), all.size() * sizeof(EkInstr), cudaMemcpyHostToDevice));
+    }
+    if (need_lit) {
+        ek_cuda_check(cudaMalloc(&e.d_lit, std::max<size_t>(a.lits.size(), 1) * 4));
+        if (!a.lits.empty()) ek_cuda_check(cudaMemcpy(e.d_lit, a.lits.data(), a.lits.size() * 4, cudaMemcpyHostToDevice));
+    }
     d_prog = e.d_prog; d_lit = e.d_lit;
-    bucket.push_back(std::move(e));
+    ctx.programs[h].push_back(std::move(e));
 }
 
 const char *dop_name(uint16_t op) {
@@ -1240,9 +1413,14 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
 
     Planner plan(ctx);
     std::vector<uint32_t> kept_literals;
+    /* Roots are planned in CREATION order: the reference walks a std::set of monotonically increasing ids
+       (jit.cu:1385-1416), so of two scatters into the same target the one recorded later runs later and wins, a
+       scatter recorded after a gather from the same array comes after it, and so on.  Handles are recycled here, so
+       the order is the per-variable sequence number, not the handle. */
     std::vector<uint32_t> work(ctx.live.begin(), ctx.live.end());
+    std::sort(work.begin(), work.end(), [&](uint32_t a, uint32_t b) { return ctx.vars[a].seq > ctx.vars[b].seq; });
     std::vector<uint32_t> roots = work;
-    while (!work.empty()) {
+    while (!work.empty()) {                              /* (pop_back: oldest first) */
         uint32_t idx = work.back(); work.pop_back();
         const EkVariable &v = ctx.vars[idx];
         if (!v.used) continue;
@@ -1264,6 +1442,12 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
         if (g.size > 0xffffffffull) { asm_error = "arrays with more than 2^32-1 entries are not supported (jit.cu:1066,1090)"; return false; }
         Assembler as(ctx, g, plan.forced, dry);
         bool ok = as.run();
+        if (ok && !as.out.has64 && !as.out.noncore) {
+            std::vector<EkInstr> lowered;
+            as.out.fast_ok = lower_fast(as.out.init, as.out, nullptr, lowered) && lower_fast(as.out.body, as.out, nullptr, lowered) &&
+                             lower_fast(as.out.fini, as.out, nullptr, lowered);
+            as.out.fast_len = (uint32_t) lowered.size();
+        }
         Config cfg; std::string cerr;
         if (ok && !choose_config(ctx, as.out, g.size, cfg, cerr)) { ok = false; as.out.error = cerr; as.out.resource_error = true; }
         if (ok) { launches.emplace_back(&g, std::move(as.out)); return true; }
@@ -1318,7 +1502,39 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
                 for (size_t i = 0; i < a.scalars.size(); ++i) oss << (i ? "," : "") << "[" << a.scalars[i].var << "," << (int) ctx.vars[a.scalars[i].var].type << "]";
                 oss << "],\"outputs\":[";
                 for (size_t i = 0; i < a.outputs.size(); ++i) oss << (i ? "," : "") << "[" << a.outputs[i].var << "," << a.outputs[i].argw << "," << a.outputs[i].bytes << "," << (int) ctx.vars[a.outputs[i].var].type << "]";
-                oss << "]}";
+                oss << "]";
+                /* the program as the 32-bit fast kernel would receive it (lower_fast), when that is the kernel the
+                   launcher would pick for this sweep */
+                Config fcfg; std::string ferr;
+                /* (judged as a wide sweep whatever its size, so that small CPU test cases exercise the lowering too) */
+                if (choose_config(ctx, a, std::max<size_t>(l.first->size, 4097), fcfg, ferr) && fcfg.V == 16) {
+                    std::vector<EkInstr> fi, fb, ff;
+                    if (lower_fast(a.init, a, &fcfg, fi) && lower_fast(a.body, a, &fcfg, fb) && lower_fast(a.fini, a, &fcfg, ff)) {
+                        oss << ",\"fast\":{\"T\":" << fcfg.T << ",\"off_slots\":" << fcfg.off_slots << ",\"n_tmp\":" << a.n_tmp;
+                        auto fsec = [&](const char *name, const std::vector<EkInstr> &v) {
+                            oss << ",\"" << name << "\":[";
+                            /* (fop, fflags, b, c, dst, aux, imm): see the field shuffle in lower_fast */
+                            for (size_t i = 0; i < v.size(); ++i)
+                                oss << (i ? "," : "") << "[" << v[i].op << "," << v[i].flags << "," << v[i].dst << "," << v[i].b << "," << v[i].c << "," << v[i].a << "," << v[i].imm << "]";
+                            oss << "]";
+                        };
+                        fsec("init", fi); fsec("body", fb); fsec("fini", ff);
+                        oss << "}";
+                    }
+                }
+                oss << "}";
+            }
+            oss << "],\"fops\":[";
+            {
+                static const char *fnames[] = { "NOP",
+#define X(n) #n, #n "_U",
+                    EK_FOPS2(X)
+#undef X
+#define X(n) #n,
+                    EK_FOPS1(X) EK_FOPS0(X)
+#undef X
+                };
+                for (int k = 0; k < FOP__COUNT; ++k) oss << (k ? "," : "") << "\"" << fnames[k] << "\"";
             }
             oss << "]}";
         } else {
@@ -1347,8 +1563,10 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
             if (v.data == nullptr) { v.data = ek_malloc(o.bytes); v.free_data = true; v.subtree_size = 1; }
         }
 
-        /* operand codes -> (byte offset >> 4) for this configuration's shared-memory layout */
-        {
+        /* operand codes -> (byte offset >> 4) for this configuration's shared-memory layout (general kernels; the fast
+           kernel's program is lowered from the symbolic form further down) */
+        const bool fast = cfg.V == 16;
+        if (!fast) {
             const uint32_t slot_bytes = cfg.T * cfg.V * 4u;
             auto patch = [&](uint16_t code) -> uint16_t {
                 if (code == EK_OPND_NONE || (code & EK_OPND_UNI)) return code;      /* uniform index == offset >> 4 */
@@ -1366,8 +1584,24 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
         }
         EkSweepArgs args;
         memset(&args, 0, sizeof(args));
-        lookup_program(ctx, a, args.prog, args.lit);
-        args.n_init = (uint32_t) a.init.size(); args.n_body = (uint32_t) a.body.size(); args.n_fini = (uint32_t) a.fini.size();
+        std::vector<EkInstr> lowered_init, lowered_body, lowered_fini;
+        if (fast) {
+            if (!lower_fast(a.init, a, &cfg, lowered_init) || !lower_fast(a.body, a, &cfg, lowered_body) || !lower_fast(a.fini, a, &cfg, lowered_fini) ||
+                lowered_init.size() + lowered_body.size() + lowered_fini.size() > EK_INLINE_PROG) {
+                ek_set_error("ek_eval(): internal error: fast-kernel lowering failed after it had been checked"); return -1;
+            }
+        }
+        const std::vector<EkInstr> &p_init = fast ? lowered_init : a.init, &p_body = fast ? lowered_body : a.body, &p_fini = fast ? lowered_fini : a.fini;
+        const size_t n_prog_total = p_init.size() + p_body.size() + p_fini.size();
+        const bool inline_prog = n_prog_total <= EK_INLINE_PROG;
+        const bool inline_lit = a.lits.size() <= EK_MAX_LIT_INLINE;
+        /* programs and literals that fit the kernel parameters travel there: nothing is uploaded and nothing is cached
+           (a trace whose literals change from step to step -- a step counter, a learning-rate schedule -- used to add a
+           cache entry and two synchronous uploads per step) */
+        if (!inline_prog || !inline_lit) lookup_program(ctx, a, !inline_prog, !inline_lit, args.prog, args.lit);
+        if (inline_lit && !a.lits.empty()) memcpy(args.lit_inline, a.lits.data(), a.lits.size() * 4);
+        if (inline_lit) args.lit = nullptr;
+        args.n_init = (uint32_t) p_init.size(); args.n_body = (uint32_t) p_body.size(); args.n_fini = (uint32_t) p_fini.size();
         args.n_lit = (uint32_t) a.lits.size();
         args.n_argw = (uint32_t) a.argw.size();
         args.n_scalar = (uint32_t) a.scalars.size();
@@ -1398,6 +1632,7 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
             args.scalar_type[k] = (uint8_t) v.type;
         }
         memcpy(args.argw, a.argw.data(), a.argw.size() * 4);
+        layout_extra(a, cfg, args.argw);             /* (fast kernel: offsets / copy counts of its own layout) */
         for (const auto &pf : a.ptr_fix) {
             uint64_t p = (uint64_t) (uintptr_t) ctx.vars[pf.var].data;
             args.argw[pf.argw] = (uint32_t) p; args.argw[pf.argw + 1] = (uint32_t) (p >> 32);
@@ -1412,20 +1647,18 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
         if (ctx.log_level >= 3) { std::ostringstream oss; dump_program(oss, a, g); fputs(oss.str().c_str(), stderr); }
 
         if (ctx.timing) ek_cuda_check(cudaEventRecord(ctx.ev_start, ctx.stream));
-        /* measured on B200: the mid-tile CTA barrier the early release needs costs more than the hidden TMA
-           latency gains (0.467 ms vs 0.400 ms on C2) -- kept behind EK_REL=1 for experiments */
-        static const bool use_rel = getenv("EK_REL") != nullptr;
-        if (use_rel && cfg.stages == 1 && a.release_at >= 0) { a.body[a.release_at].flags |= EKF_REL; args.release_mask = a.release_mask; }
-        size_t n_prog_total = a.init.size() + a.body.size() + a.fini.size();
-        bool inline_prog = n_prog_total <= EK_INLINE_PROG;
         if (inline_prog) {
             EkInstr *dstp = args.prog_inline;
-            for (const EkInstr &in : a.init) *dstp++ = in;
-            for (const EkInstr &in : a.body) *dstp++ = in;
-            for (const EkInstr &in : a.fini) *dstp++ = in;
+            for (const EkInstr &in : p_init) *dstp++ = in;
+            for (const EkInstr &in : p_body) *dstp++ = in;
+            for (const EkInstr &in : p_fini) *dstp++ = in;
         }
-        const bool core32 = !a.has64 && !a.noncore && inline_prog;     /* 32-bit-only program: kernels without high planes */
-        ek_cuda_check(ek_launch_sweep(cfg.V, inline_prog, core32, args, grid, cfg.T, cfg.smem, ctx.stream));
+        if (fast) {
+            ek_cuda_check(ek_launch_sweep_fast(args, grid, cfg.T, cfg.smem, ctx.stream));
+        } else {
+            const bool core32 = !a.has64 && !a.noncore && inline_prog;     /* 32-bit-only program: kernels without high planes */
+            ek_cuda_check(ek_launch_sweep(cfg.V, inline_prog, core32, args, grid, cfg.T, cfg.smem, ctx.stream));
+        }
         if (ctx.timing) {
             ek_cuda_check(cudaEventRecord(ctx.ev_stop, ctx.stream));
             ek_cuda_check(cudaEventSynchronize(ctx.ev_stop));

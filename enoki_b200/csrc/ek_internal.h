@@ -29,6 +29,7 @@ struct EkVariable {
     void    *data = nullptr;
     uint32_t ref_ext = 0, ref_int = 0;
     uint32_t subtree_size = 0;
+    uint64_t seq = 0;                   /* creation order (handles are recycled, so a handle says nothing about age) */
     bool side_effect = false;
     bool dirty = false;
     bool free_data = true;
@@ -57,6 +58,7 @@ struct EkContext {
     std::vector<EkVariable> vars;       /* index = handle */
     std::vector<uint32_t> free_handles;
     std::set<uint32_t> live;            /* jit.cu:166-167 */
+    uint64_t next_seq = 1;              /* EkVariable::seq counter */
     std::vector<uint32_t> dirty;        /* jit.cu:169-170 */
     std::unordered_map<const void *, uint32_t> ptr_map;    /* jit.cu:178-179 */
     uint32_t scatter_gather_operand = 0;
@@ -99,6 +101,8 @@ void ek_cuda_check_impl(cudaError_t err, const char *file, int line);
 /* kernels (defined in .cu files) */
 cudaError_t ek_launch_sweep(int V, bool inline_prog, bool core32, const EkSweepArgs &args, unsigned grid, unsigned block,
                             size_t smem_bytes, cudaStream_t stream);
+/* 32-bit fast kernel (ek_sweep_fast.cu): args.prog_inline holds the lowered program; block = 128 or 256 */
+cudaError_t ek_launch_sweep_fast(const EkSweepArgs &args, unsigned grid, unsigned block, size_t smem_bytes, cudaStream_t stream);
 void ek_launch_fill(void *ptr, size_t elem_size, uint64_t value, size_t n, cudaStream_t stream);
 void ek_launch_reverse(void *out, const void *in, size_t elem_size, size_t n, cudaStream_t stream);
 void ek_launch_flush(void *buf, size_t bytes, cudaStream_t stream);

@@ -138,17 +138,71 @@ enum EkDop : uint16_t {
     DOP__COUNT
 };
 
+/* ---- lowered instruction format of the 32-bit fast kernel (ek_sweep_fast.cu) ----
+   The assembler's EkInstr stream is lowered once more at launch time (ek_eval.cpp: lower_fast): the fused accumulator
+   load and the -x / |x| input modifiers become instructions of their own (the dispatch frame then never writes the
+   accumulator, which is what lets ptxas keep it in one fixed register set), operand codes become absolute
+   shared-memory offsets, and operations whose second operand is a literal / scalar pick a "_U" twin that reads ONE
+   word from the uniform pool instead of staging 16 registers.
+     x = fop | fflags << 16      y = b | c << 16      z = dst | aux << 16      w = imm
+   b, c, dst: shared-memory byte offset >> 4 (per-thread operands: + 16 * tid, + 16 * T per 128-bit group), or a
+   uniform-pool word index; aux: reduction kind | class << 8 (FF_RACC).  Same 16 bytes as EkInstr. */
+#define FF_B    0x0001u   /* fetch per-thread operand B                                         */
+#define FF_C    0x0002u   /* fetch per-thread operand C                                         */
+#define FF_BU   0x0004u   /* broadcast uniform-pool word b into B (ops without a _U twin)       */
+#define FF_CU   0x0008u   /* broadcast uniform-pool word c into C                               */
+#define FF_ST   0x0010u   /* store the accumulator to slot dst                                  */
+#define FF_STG  0x0020u   /* store the accumulator to the global array whose pointer is pool pair imm */
+#define FF_RACC 0x0040u   /* fold the accumulator into the reduction partials in slot dst       */
+#define FF_VU   0x0080u   /* scatters: the value operand is the uniform-pool word b             */
+#define FF_MU   0x0100u   /* gathers / scatters: the mask operand is the uniform-pool word (b for gathers, c for scatters) */
+#define FF_POST (FF_ST | FF_STG | FF_RACC)
+
+/* binary operations: every entry X has a twin X_U = X + 1 whose second operand is uniform-pool word b */
+#define EK_FOPS2(X) \
+    X(ADD_F32) X(SUB_F32) X(SUBR_F32) X(MUL_F32) X(DIV_F32) X(MIN_F32) X(MAX_F32) X(MULNZ_F32) \
+    X(LT_F32) X(LE_F32) X(GT_F32) X(GE_F32) X(EQ_F32) X(NE_F32) \
+    X(ADD_I32) X(SUB_I32) X(SUBR_I32) X(MUL_I32) X(MIN_I32) X(MIN_U32) X(MAX_I32) X(MAX_U32) \
+    X(SHL_32) X(SHR_I32) X(SHR_U32) X(AND_32) X(OR_32) X(XOR_32) \
+    X(LT_I32) X(LE_I32) X(GT_I32) X(GE_I32) X(LT_U32) X(LE_U32) X(GT_U32) X(GE_U32) X(EQ_32) X(NE_32)
+/* everything else that may appear in a body */
+#define EK_FOPS1(X) \
+    X(FMA_F32) X(FMA_F32_UB) X(FMA_F32_UC) X(FMAC_F32) X(FMAC_F32_UB) \
+    X(MAD_I32) X(MADC_I32) X(FMANZ_F32) X(FMANZC_F32) X(SEL_M_32) X(SEL_T_32) X(SEL_F_32) \
+    X(ABS_F32) X(NEG_F32) X(SQRT_F32) X(RCP_F32) X(RSQRT_F32) X(EXP_F32) X(LOG_F32) X(SIN_F32) X(COS_F32) \
+    X(FLOOR_F32) X(CEIL_F32) X(ROUND_F32) X(TRUNC_F32) X(ABS_I32) X(NEG_I32) X(NOT_32) X(NOT_B) X(NEZ_32) \
+    X(CVT_F32_I32) X(CVT_F32_U32) X(CVT_I32_F32) X(CVT_U32_F32) \
+    X(LOAD) X(LOADU) X(INDEX) X(LD_U8) X(LD_S8) X(LDG_32) X(ST_32) X(ST_8) \
+    X(GATHER_32) X(GATHER_32_SMEM) X(SCATTER_32) X(SCATTER_ADD_F32) X(SCATTER_ADD_I32) \
+    X(SCATTER_ADD_F32_SMEM) X(SCATTER_ADD_I32_SMEM) X(RACC)
+/* init / fini sections only (interpreted outside the hot loop) */
+#define EK_FOPS0(X) \
+    X(SMEM_ZERO) X(SMEM_LOAD_TABLE) X(SMEM_FLUSH_ADD_F32) X(SMEM_FLUSH_ADD_I32) X(RFIN)
+
+enum EkFop : uint16_t {
+    FOP_NOP,
+#define X(n) FOP_##n, FOP_##n##_U,
+    EK_FOPS2(X)
+#undef X
+#define X(n) FOP_##n,
+    EK_FOPS1(X)
+    EK_FOPS0(X)
+#undef X
+    FOP__COUNT
+};
+
 /* ---- launch arguments (passed by value as a __grid_constant__ kernel parameter) ---- */
 #define EK_MAX_STAGED   16      /* staged (TMA) input arrays per sweep                  */
 #define EK_MAX_ARGW     448     /* argument words appended to the uniform pool          */
 #define EK_MAX_SCALAR   64      /* size-1 evaluated inputs fetched in the prologue      */
+#define EK_MAX_LIT_INLINE 128   /* literal words carried inside the kernel parameters       */
 #define EK_INLINE_PROG  448     /* instructions carried inside the kernel parameters (constant bank):
                                    instruction words are then uniform registers -> uniform branches */
 
 struct EkSweepArgs {
     const EkInstr  *prog;          /* [n_init | n_body | n_fini] instructions (device memory; used when
                                       the program does not fit prog_inline)                   */
-    const uint32_t *lit;           /* literal words (device memory, cached with the program)  */
+    const uint32_t *lit;           /* literal words (device memory, cached with the program); NULL: lit_inline */
     uint32_t n_init, n_body, n_fini;
     uint32_t n_lit;                /* literal words -> uniform pool [0, n_lit)               */
     uint32_t n_argw;               /* argument words -> uniform pool [n_lit, n_lit+n_argw)   */
@@ -175,5 +229,6 @@ struct EkSweepArgs {
     const void *scalar_ptr[EK_MAX_SCALAR];
     uint8_t     scalar_type[EK_MAX_SCALAR];   /* ek_type                                      */
     uint32_t    argw[EK_MAX_ARGW];
+    uint32_t    lit_inline[EK_MAX_LIT_INLINE]; /* literal words when they fit (nothing is uploaded, nothing is cached) */
     EkInstr     prog_inline[EK_INLINE_PROG];   /* valid when the launcher picks the INLINE kernel */
 };

@@ -276,6 +276,7 @@ static uint32_t var_new(ek_type type) {
     EkVariable &v = ctx.vars[idx];
     v = EkVariable();
     v.type = type; v.used = true;
+    v.seq = ctx.next_seq++;
     return idx;
 }
 
@@ -545,7 +546,11 @@ uint32_t ek_trace_append(ek_type type, ek_op op, uint32_t a, uint32_t b, uint32_
 uint32_t ek_var_set_size(uint32_t index, size_t size, int copy) {
     EkVariable *v = var_get(index, "ek_var_set_size()"); if (!v) return 0;
     if (v->size == size) return index;
-    if (v->data != nullptr || v->ref_int > 0) {
+    /* lazy reductions (hsum ... count) are size-1 results of a sweep over their operand: like an evaluated scalar they
+       can only be widened through a broadcasting MOV, never in place (the reference evaluates them eagerly, so there
+       the variable has data and takes this branch anyway) */
+    const bool lazy_reduce = v->op >= EK_OP_HSUM && v->op <= EK_OP_COUNT;
+    if (v->data != nullptr || v->ref_int > 0 || lazy_reduce) {
         if (v->size == 1 && copy) {                                                             /* jit.cu:357-364 */
             uint32_t nidx = ek_trace_append(v->type, EK_OP_MOV, index, 0, 0, 0);
             if (!nidx) return 0;

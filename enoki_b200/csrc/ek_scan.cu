@@ -31,7 +31,7 @@ template <typename T> __device__ __forceinline__ T warp_incl_scan(T v) {
 
 /* inclusive scan of one value per thread across the CTA; returns the CTA total in `total` */
 template <typename T> __device__ __forceinline__ T block_incl_scan(T v, T &total) {
-    __shared__ unsigned char raw[32 * sizeof(T) + sizeof(T)];
+    __shared__ __align__(16) unsigned char raw[32 * sizeof(T) + sizeof(T)];
     T *warp_tot = reinterpret_cast<T *>(raw);
     unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     T s = warp_incl_scan(v);
@@ -144,112 +144,6 @@ template <typename T> int compress_impl(size_t n, const void *data, const uint8_
 }
 
 
-/* ---------------- partition (virtual-call dispatch) ---------------- */
-constexpr uint32_t PART_SLOTS = 2048, PART_MAX_UNIQUE = 1024, PART_CHUNK = 1024;
-struct PartTable {
-    unsigned long long key[PART_SLOTS];
-    uint32_t count[PART_SLOTS];
-    uint32_t used[PART_SLOTS];
-    uint32_t n_used, overflow;
-};
-__device__ __forceinline__ uint32_t part_hash(uint64_t k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 29;
-    return (uint32_t) k & (PART_SLOTS - 1);
-}
-/* distinct pointer values + their counts: lanes holding the same value are combined first (one table update per
-   distinct value per warp) */
-__global__ void __launch_bounds__(256) part_discover(const uint64_t *keys, uint32_t n, PartTable *tab) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_round = (n + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool active = i < n;
-        const unsigned amask = __ballot_sync(0xffffffffu, active);
-        if (!active) continue;
-        const uint64_t k = keys[i];
-        const unsigned peers = __match_any_sync(amask, k);
-        if (lane != (uint32_t) (__ffs(peers) - 1)) continue;
-        /* open addressing with ONE compare-and-swap per probe and no waiting: a slot holds key + 1 (0 = empty; ~0 is
-           not a pointer value), so claiming a slot and publishing its key are the same atomic operation */
-        uint32_t h = part_hash(k);
-        const uint32_t c = (uint32_t) __popc(peers);
-        for (uint32_t probe = 0; probe < PART_SLOTS; ++probe, h = (h + 1) & (PART_SLOTS - 1)) {
-            const unsigned long long prev = atomicCAS(&tab->key[h], 0ull, (unsigned long long) k + 1ull);
-            if (prev == 0ull) {                                /* first sighting of this value */
-                tab->used[h] = 1u;
-                if (atomicAdd(&tab->n_used, 1u) >= PART_MAX_UNIQUE) tab->overflow = 1u;
-                atomicAdd(&tab->count[h], c);
-                break;
-            }
-            if (prev == (unsigned long long) k + 1ull) { atomicAdd(&tab->count[h], c); break; }
-            if (tab->overflow) break;
-        }
-    }
-}
-/* index of `k` in the sorted distinct values (always present) */
-__device__ __forceinline__ uint32_t part_bucket(const uint64_t *sorted, uint32_t K, uint64_t k) {
-    uint32_t lo = 0, hi = K;
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (sorted[mid] <= k) lo = mid; else hi = mid; }
-    return lo;
-}
-/* one warp per chunk of PART_CHUNK consecutive indices: bucket histogram of the chunk */
-__global__ void __launch_bounds__(32) part_count(const uint64_t *keys, uint32_t n, const uint64_t *uniq, uint32_t K, uint32_t *hist) {
-    extern __shared__ unsigned long long part_smem[];
-    uint64_t *sk = reinterpret_cast<uint64_t *>(part_smem);
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(sk + K);
-    for (uint32_t k = threadIdx.x; k < K; k += 32u) { sk[k] = uniq[k]; cnt[k] = 0u; }
-    __syncwarp();
-    const uint32_t base = blockIdx.x * PART_CHUNK;
-    for (uint32_t j = threadIdx.x; j < PART_CHUNK; j += 32u) {
-        const uint32_t i = base + j;
-        if (i < n) atomicAdd(&cnt[part_bucket(sk, K, keys[i])], 1u);
-    }
-    __syncwarp();
-    for (uint32_t k = threadIdx.x; k < K; k += 32u) hist[(size_t) blockIdx.x * K + k] = cnt[k];
-}
-/* per bucket (one CTA each): exclusive scan of the chunk counts -> first output position of every chunk */
-__global__ void __launch_bounds__(256) part_scan(uint32_t *hist, uint32_t n_chunks, uint32_t K) {
-    const uint32_t k = blockIdx.x;
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0u;
-    __syncthreads();
-    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 256u) {
-        const uint32_t c = c0 + threadIdx.x;
-        uint32_t v = c < n_chunks ? hist[(size_t) c * K + k] : 0u, total;
-        uint32_t incl = block_incl_scan(v, total);
-        const uint32_t base = carry;
-        if (c < n_chunks) hist[(size_t) c * K + k] = base + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry = base + total;
-        __syncthreads();
-    }
-}
-/* one warp per chunk, 32 consecutive indices at a time: rank inside the step from a warp vote, running
-   per-bucket positions in shared memory -> indices of a bucket come out in ascending order */
-__global__ void __launch_bounds__(32) part_scatter(const uint64_t *keys, uint32_t n, const uint64_t *uniq, uint32_t K,
-                                                   const uint32_t *hist, uint32_t *const *dst) {
-    extern __shared__ unsigned long long part_smem[];
-    uint64_t *sk = reinterpret_cast<uint64_t *>(part_smem);
-    uint32_t *pos = reinterpret_cast<uint32_t *>(sk + K);
-    for (uint32_t k = threadIdx.x; k < K; k += 32u) { sk[k] = uniq[k]; pos[k] = hist[(size_t) blockIdx.x * K + k]; }
-    __syncwarp();
-    const uint32_t base = blockIdx.x * PART_CHUNK, lane = threadIdx.x;
-    /* every warp-level primitive below is executed by all 32 lanes with the full mask (lanes past the end of the array
-       form a group of their own with the bucket id ~0): no lane ever waits at a barrier with a different mask */
-    for (uint32_t j = 0; j < PART_CHUNK; j += 32u) {
-        const uint32_t i = base + j + lane;
-        const bool active = i < n;
-        const uint32_t b = active ? part_bucket(sk, K, keys[i]) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
-        const uint32_t first = active ? pos[b] : 0u;
-        __syncwarp();                                   /* everybody has read the running positions */
-        if (active) {
-            dst[b][first + rank] = i;
-            if (rank == 0) pos[b] = first + (uint32_t) __popc(peers);
-        }
-        __syncwarp();                                   /* ... and sees the updated ones in the next step */
-    }
-}
 } // namespace
 
 extern "C" {
@@ -278,89 +172,121 @@ int ek_compress(ek_type type, size_t n, const void *data, const uint8_t *mask, v
     }
 }
 
-/* cuda_partition (horiz.cu:35-122): groups the indices 0..n-1 by pointer value.  The reference radix-sorts all
-   (pointer, index) pairs; virtual-call dispatch (array_call.h:147-165) only ever sees a handful of distinct
-   instances, so this is (1) one pass that collects the distinct pointers and their counts in a small hash table,
-   (2) a host sort of those few values, (3) a stable multi-way scatter of the indices (per-chunk bucket histograms,
-   per-bucket scan over chunks, in-order ranking inside a chunk with warp votes).  Same results as the stable
-   sort: unique pointers ascending, indices ascending inside every group.  More than PART_MAX_UNIQUE distinct
-   values fall back to a host-side stable sort. */
-int ek_partition(size_t n, const void **ptrs, void ***unique_out, uint32_t **counts_out, uint32_t ***perm_out) {
-    /* Round-1 status: written and compiled, NOT yet verified on hardware -- the first two GPU runs of
-       tests/cpp/call_check ended with the loss of the GPU box after ~2 minutes (a hung kernel).  The likely cause was
-       found by inspection afterwards and fixed: part_scatter synchronised the lanes of a ragged last step with
-       __syncwarp(active-mask) inside a branch while the inactive lanes waited at __syncwarp(full mask) -- undefined
-       behaviour that only shows when n is not a multiple of 32 (it was 100003); every warp primitive there now runs
-       on all 32 lanes with the full mask.  No GPU time was left to confirm it, so the entry point keeps its
-       documented round-1 behaviour (an error) unless EK_ENABLE_PARTITION=1 is set; tests/test_gpu_eval.py::test_partition
-       and tests/cpp/call_check are the checks to run first in round 2 (under a short timeout). */
-    if (getenv("EK_ENABLE_PARTITION") == nullptr) {
-        ek_set_error("ek_partition(): not enabled (unverified in this round; set EK_ENABLE_PARTITION=1 to try it, SURVEY.md 8f row 1)");
-        return -1;
+/* cuda_partition (horiz.cu:35-122): groups the indices 0..n-1 by pointer value -- unique pointers ascending, indices
+   ascending inside every group (what the reference's stable radix sort + run-length encode produce).
+
+   Virtual-call dispatch (array_call.h:147-165) only ever sees a handful of distinct instances, so the grouping is
+   composed from the two device primitives of this backend that are already pinned by the parity tests -- no kernel
+   of its own:
+     (1) distinct values, ascending:  v_0 = hmin(ptr);  v_{k+1} = hmin(select(ptr > v_k, ptr, ~0))   (fused sweep +
+         reduction epilogue, one 8-byte read-back per value),
+     (2) per value: mask = (ptr == v_k) recorded through the evaluator, indices = compress(arange(n), mask)
+         (ek_compress: three-phase scan, output order = input order, i.e. ascending).
+   Cost: 2 K passes over the pointer array for K distinct values.  More than EK_PART_MAX_GROUPS distinct values (not a
+   dispatch-shaped input) take a host-side stable sort of the downloaded pointers, as do inputs when
+   EK_PARTITION_HOST=1 is set.
+
+   History: round 1 shipped a dedicated hash + multi-way scatter kernel set for this; three GPU boxes were lost on
+   its first runs (rounds 1 and 2), it was never seen to pass, and it has been removed. */
+namespace {
+constexpr size_t EK_PART_MAX_GROUPS = 256;
+
+struct Handle {             /* scoped external reference on a trace variable */
+    uint32_t h = 0;
+    Handle() = default;
+    explicit Handle(uint32_t v) : h(v) {}
+    Handle(const Handle &) = delete; Handle &operator=(const Handle &) = delete;
+    Handle(Handle &&o) noexcept : h(o.h) { o.h = 0; }
+    Handle &operator=(Handle &&o) noexcept { if (this != &o) { reset(); h = o.h; o.h = 0; } return *this; }
+    ~Handle() { reset(); }
+    void reset() { if (h) ek_dec_ref_ext(h); h = 0; }
+    explicit operator bool() const { return h != 0; }
+};
+
+int partition_host_sort(EkContext &ctx, size_t n, const uint64_t *keys, std::vector<uint64_t> &uniq,
+                        std::vector<uint32_t> &cnts, uint32_t **&perm_h) {
+    std::vector<uint64_t> hk(n);
+    ek_cuda_check(cudaMemcpyAsync(hk.data(), keys, n * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    ek_cuda_check(cudaStreamSynchronize(ctx.stream));
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t) i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hk[a] < hk[b]; });
+    std::vector<size_t> starts;
+    for (size_t i = 0; i < n; ++i) if (i == 0 || hk[order[i]] != hk[order[i - 1]]) { starts.push_back(i); uniq.push_back(hk[order[i]]); }
+    starts.push_back(n);
+    perm_h = (uint32_t **) malloc(sizeof(uint32_t *) * uniq.size());
+    for (size_t k = 0; k < uniq.size(); ++k) {
+        uint32_t c = (uint32_t) (starts[k + 1] - starts[k]);
+        cnts.push_back(c);
+        perm_h[k] = (uint32_t *) ek_malloc((size_t) c * 4);
+        ek_cuda_check(cudaMemcpyAsync(perm_h[k], order.data() + starts[k], (size_t) c * 4, cudaMemcpyHostToDevice, ctx.stream));
     }
+    ek_cuda_check(cudaStreamSynchronize(ctx.stream));
+    return 0;
+}
+} // namespace
+
+int ek_partition(size_t n, const void **ptrs, void ***unique_out, uint32_t **counts_out, uint32_t ***perm_out) {
     if (ek_init() != 0) return -1;
     EkContext &ctx = ek_ctx();
     if (n == 0 || n > 0xffffffffull) { ek_set_error("ek_partition(): unsupported size"); return -1; }
     const uint64_t *keys = reinterpret_cast<const uint64_t *>(ptrs);
     std::vector<uint64_t> uniq;
     std::vector<uint32_t> cnts;
-
-    /* (1) distinct values */
-    PartTable *tab = (PartTable *) ek_malloc(sizeof(PartTable));
-    PartTable *tab_h = (PartTable *) ek_host_malloc(sizeof(PartTable));
-    ek_cuda_check(cudaMemsetAsync(tab, 0, sizeof(PartTable), ctx.stream));
-    unsigned grid = (unsigned) std::min<size_t>((n + 255) / 256, (size_t) ctx.num_sms * 8);
-    part_discover<<<grid, 256, 0, ctx.stream>>>(keys, (uint32_t) n, tab);
-    ek_cuda_check(cudaGetLastError());
-    ek_cuda_check(cudaMemcpyAsync(tab_h, tab, sizeof(PartTable), cudaMemcpyDeviceToHost, ctx.stream));
-    ek_cuda_check(cudaStreamSynchronize(ctx.stream));
-    bool overflow = tab_h->overflow != 0;
-    if (!overflow) {
-        std::vector<std::pair<uint64_t, uint32_t>> found;
-        for (uint32_t i = 0; i < PART_SLOTS; ++i) if (tab_h->key[i]) found.emplace_back(tab_h->key[i] - 1ull, tab_h->count[i]);
-        std::sort(found.begin(), found.end());
-        for (auto &f : found) { uniq.push_back(f.first); cnts.push_back(f.second); }
-    }
-    ek_free(tab); ek_host_free(tab_h);
-
     uint32_t **perm_h = nullptr;
-    if (!overflow) {
-        const uint32_t K = (uint32_t) uniq.size();
-        perm_h = (uint32_t **) malloc(sizeof(uint32_t *) * K);
-        for (uint32_t k = 0; k < K; ++k) perm_h[k] = (uint32_t *) ek_malloc((size_t) cnts[k] * 4);
-        /* (3) stable scatter */
-        const uint32_t n_chunks = (uint32_t) ((n + PART_CHUNK - 1) / PART_CHUNK);
-        uint64_t *d_uniq = (uint64_t *) ek_malloc((size_t) K * 8);
-        uint32_t **d_dst = (uint32_t **) ek_malloc((size_t) K * sizeof(uint32_t *));
-        uint32_t *d_hist = (uint32_t *) ek_malloc((size_t) n_chunks * K * 4);
-        ek_cuda_check(cudaMemcpyAsync(d_uniq, uniq.data(), (size_t) K * 8, cudaMemcpyHostToDevice, ctx.stream));
-        ek_cuda_check(cudaMemcpyAsync(d_dst, perm_h, (size_t) K * sizeof(uint32_t *), cudaMemcpyHostToDevice, ctx.stream));
-        const size_t smem = (size_t) K * 12;       /* sorted keys + counters */
-        part_count<<<n_chunks, 32, smem, ctx.stream>>>(keys, (uint32_t) n, d_uniq, K, d_hist);
-        part_scan<<<K, 256, 0, ctx.stream>>>(d_hist, n_chunks, K);
-        part_scatter<<<n_chunks, 32, smem, ctx.stream>>>(keys, (uint32_t) n, d_uniq, K, d_hist, d_dst);
-        ek_cuda_check(cudaGetLastError());
-        ek_cuda_check(cudaStreamSynchronize(ctx.stream));   /* the host vectors above are pageable */
-        ek_free(d_uniq); ek_free(d_dst); ek_free(d_hist);
-    } else {
-        /* many distinct values: host-side stable sort (not a dispatch-shaped input) */
-        std::vector<uint64_t> hk(n);
-        ek_cuda_check(cudaMemcpyAsync(hk.data(), keys, n * 8, cudaMemcpyDeviceToHost, ctx.stream));
-        ek_cuda_check(cudaStreamSynchronize(ctx.stream));
-        std::vector<uint32_t> order(n);
-        for (size_t i = 0; i < n; ++i) order[i] = (uint32_t) i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hk[a] < hk[b]; });
-        std::vector<size_t> starts;
-        for (size_t i = 0; i < n; ++i) if (i == 0 || hk[order[i]] != hk[order[i - 1]]) { starts.push_back(i); uniq.push_back(hk[order[i]]); }
-        starts.push_back(n);
-        perm_h = (uint32_t **) malloc(sizeof(uint32_t *) * uniq.size());
-        for (size_t k = 0; k < uniq.size(); ++k) {
-            uint32_t c = (uint32_t) (starts[k + 1] - starts[k]);
-            cnts.push_back(c);
-            perm_h[k] = (uint32_t *) ek_malloc((size_t) c * 4);
-            ek_cuda_check(cudaMemcpyAsync(perm_h[k], order.data() + starts[k], (size_t) c * 4, cudaMemcpyHostToDevice, ctx.stream));
+    bool host = getenv("EK_PARTITION_HOST") != nullptr;
+
+    if (!host) {
+        /* borrow the caller's array as a trace variable (jit.cu:373-395 with dealloc = false) */
+        Handle kv(ek_var_register(EK_UINT64, n, const_cast<void *>((const void *) ptrs), 0));
+        if (!kv) return -1;
+        auto lit64 = [](uint64_t v) { return Handle(ek_trace_append(EK_UINT64, EK_OP_LITERAL, 0, 0, 0, v)); };
+        /* (1) distinct values in ascending order */
+        bool have_prev = false; uint64_t prev = 0;
+        while (true) {
+            Handle m;
+            if (!have_prev) {
+                m = Handle(ek_trace_append(EK_UINT64, EK_OP_HMIN, kv.h, 0, 0, 0));
+            } else {
+                Handle lp = lit64(prev), top = lit64(~0ull);
+                Handle gt(ek_trace_append(EK_BOOL, EK_OP_GT, kv.h, lp.h, 0, 0));
+                if (!lp || !top || !gt) return -1;
+                Handle cand(ek_trace_append(EK_UINT64, EK_OP_SELECT, gt.h, kv.h, top.h, 0));
+                if (!cand) return -1;
+                m = Handle(ek_trace_append(EK_UINT64, EK_OP_HMIN, cand.h, 0, 0, 0));
+            }
+            if (!m || ek_eval_var(m.h) != 0) return -1;
+            uint64_t v = 0;
+            if (ek_fetch_element(&v, m.h, 0, 8) != 0) return -1;
+            if (have_prev && v == ~0ull) break;
+            uniq.push_back(v); prev = v; have_prev = true;
+            if (v == ~0ull) break;                         /* (not a pointer value; nothing can follow it) */
+            if (uniq.size() > EK_PART_MAX_GROUPS) { host = true; break; }
         }
-        ek_cuda_check(cudaStreamSynchronize(ctx.stream));
+        if (!host) {
+            /* (2) one compaction of the index sequence per distinct value */
+            Handle idx(ek_trace_append(EK_UINT32, EK_OP_INDEX, 0, 0, 0, 0));
+            if (!idx || ek_var_set_size(idx.h, n, 0) == 0 || ek_eval_var(idx.h) != 0) return -1;
+            perm_h = (uint32_t **) malloc(sizeof(uint32_t *) * uniq.size());
+            for (size_t k = 0; k < uniq.size(); ++k) {
+                Handle lv = lit64(uniq[k]);
+                Handle eq(ek_trace_append(EK_BOOL, EK_OP_EQ, kv.h, lv.h, 0, 0));
+                void *out = nullptr; size_t cnt = 0;
+                if (!lv || !eq || ek_eval_var(eq.h) != 0 ||
+                    ek_compress(EK_UINT32, n, ek_var_ptr(idx.h), (const uint8_t *) ek_var_ptr(eq.h), &out, &cnt) != 0) {
+                    for (size_t j = 0; j < k; ++j) ek_free(perm_h[j]);
+                    free(perm_h);
+                    return -1;
+                }
+                perm_h[k] = (uint32_t *) out;
+                cnts.push_back((uint32_t) cnt);
+            }
+            ek_cuda_check(cudaStreamSynchronize(ctx.stream));
+        }
+    }
+    if (host) {
+        uniq.clear(); cnts.clear();
+        if (partition_host_sort(ctx, n, keys, uniq, cnts, perm_h) != 0) return -1;
     }
     /* outputs with the reference's ownership: pinned-host unique / counts (counts[0] = number of groups,
        horiz.cu:83-121), malloc'd array of device permutation pointers */
@@ -370,7 +296,6 @@ int ek_partition(size_t n, const void **ptrs, void ***unique_out, uint32_t **cou
     counts_h[0] = (uint32_t) K;
     for (size_t k = 0; k < K; ++k) { counts_h[k + 1] = cnts[k]; unique_h[k] = (void *) (uintptr_t) uniq[k]; }
     *unique_out = unique_h; *counts_out = counts_h; *perm_out = perm_h;
-    ctx.stats.launches += 4;
     return 0;
 }
 

@@ -22,7 +22,62 @@ def _P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+FF_B, FF_C, FF_BU, FF_CU, FF_ST, FF_STG, FF_RACC, FF_VU, FF_MU = 1, 2, 4, 8, 0x10, 0x20, 0x40, 0x80, 0x100
+
+
+def raise_fast(fast, fop_names, op_index):
+    """The lowered program of the 32-bit fast kernel (ek_isa.h "lowered instruction format", produced by lower_fast in
+    ek_eval.cpp) translated back into (op, flags, dst, b, c, a, imm) tuples of the assembler's form, so that the same
+    per-element interpreter executes it: checks the splitting of accumulator loads / modifiers, the _U twins, the
+    operand encoding against the fast kernel's shared-memory layout and the post-action flags on the CPU."""
+    T, off_slots, n_tmp = fast["T"], fast["off_slots"], fast["n_tmp"]
+    slot_bytes = T * 16 * 4
+
+    def slot(off16):                                # byte offset >> 4 -> temporary slot / staged unit code
+        q, r = divmod((off16 << 4) - off_slots, slot_bytes)
+        assert r == 0 and q >= 0, ("operand offset is not a slot boundary", off16)
+        return q if q < n_tmp else 0x4000 | (q - n_tmp)
+
+    def uni(i):
+        return 0x8000 | i
+
+    def conv(t):
+        fop, fl, b, c, dst, aux, imm = t
+        name = fop_names[fop]
+        flags, cb, cc, ca, d = 0, OP_NONE, OP_NONE, OP_NONE, 0
+        if fl & FF_B: flags |= F_HAS_B; cb = slot(b)
+        if fl & FF_BU: flags |= F_HAS_B; cb = uni(b)
+        if fl & FF_C: flags |= F_HAS_C; cc = slot(c)
+        if fl & FF_CU: flags |= F_HAS_C; cc = uni(c)
+        if name in ("LOAD", "LOADU"):
+            flags |= F_HAS_B; cb = slot(b) if name == "LOAD" else uni(b); name = "LOAD_32"
+        elif name.endswith("_U") and name[:-2] in op_index:
+            flags |= F_HAS_B; cb = uni(b); name = name[:-2]
+        elif name == "FMA_F32_UB": flags |= F_HAS_B; cb = uni(b); name = "FMA_F32"
+        elif name == "FMA_F32_UC": flags |= F_HAS_C; cc = uni(c); name = "FMA_F32"
+        elif name == "FMAC_F32_UB": flags |= F_HAS_B; cb = uni(b); name = "FMAC_F32"
+        elif name in ("LD_U8", "LD_S8"): cb = slot(b)
+        elif name.startswith("GATHER"):
+            if fl & FF_MU: flags |= F_HAS_B; cb = uni(b)
+        elif name.startswith("SCATTER"):
+            if fl & FF_VU: flags |= F_HAS_B; cb = uni(b)
+            if fl & FF_MU: flags |= F_HAS_C; cc = uni(c)
+        elif name == "RFIN":
+            flags |= F_HAS_B; cb = slot(b); d = dst
+        if fl & FF_ST: flags |= F_ST; d = slot(dst)
+        if fl & FF_STG: flags |= F_STG
+        if fl & FF_RACC:
+            d = slot(dst)
+            if name == "RACC": imm = aux
+            else: flags |= F_RACC; ca = aux
+        return [op_index[name], flags, d, cb, cc, ca, imm]
+
+    return {k: [conv(t) for t in fast[k]] for k in ("init", "body", "fini")}
+
+
 class Emulator:
+    prefer_fast = False        # execute the lowered fast-kernel program of a sweep when the dump carries one
+
     def __init__(self, oracle, arrays, by_address=None):
         """arrays: variable index -> numpy array (data of evaluated inputs); by_address: device address -> variable index
         (gather sources / scatter targets reach the program as raw pointers, not as variables)."""
@@ -165,7 +220,12 @@ class Emulator:
 
     def run(self, program):
         names = program["ops"]
+        self.fast_sweeps = 0
         for sw in program["sweeps"]:
+            if self.prefer_fast and "fast" in sw:
+                raised = raise_fast(sw["fast"], program["fops"], {n: i for i, n in enumerate(names)})
+                sw = dict(sw, **raised)
+                self.fast_sweeps += 1
             self._sweep(names, sw)
 
     def _sweep(self, names, sw):

@@ -234,3 +234,26 @@ def test_cpp_header_shim_records_the_same_programs(ek):
     sweeps = [l for l in ph.splitlines() if l.startswith("sweep")]
     assert len(sweeps) == 2 and "phase=0" in sweeps[0] and "phase=1" in sweeps[1] and "scalars=1" in sweeps[1]
     assert "RFIN" in ph and "CVT_F32_U32" in ph and "SEL_T_32" in ph
+
+
+def test_resize_of_a_lazy_reduction_broadcasts(ek):
+    """hsum() is a lazy size-1 variable here; resize() must give a broadcasting MOV node like it does
+    for an evaluated scalar (jit.cu:357-364), not relabel the reduce node as wide (its sweep writes 8 bytes)."""
+    import gc
+    from enoki_b200 import Float32, hsum
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    x = Float32.map(0x7f0000000000, 500)
+    s = hsum(x * 2.0)
+    red = s.index
+    L = ek.lib()
+    h = L.ek_var_set_size(red, 500, 1)
+    assert h != 0 and h != red, "a new (MOV) variable is expected"
+    assert L.ek_var_size(h) == 500
+    s.index = h                                 # the call consumed the caller's reference on `red` (jit.cu:362)
+    plan = ek.debug_plan()
+    assert "n=500" in plan and "RFIN" in plan
+    # without `copy` the reference refuses to resize an (evaluated) scalar: jit.cu:366-371
+    s2 = hsum(x)
+    assert L.ek_var_set_size(s2.index, 500, 0) == 0 and b"resize" in L.ek_last_error()
+    del s, s2, x
+    gc.collect(); ek.lib().ek_debug_discard_side_effects()

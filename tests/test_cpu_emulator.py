@@ -7,6 +7,15 @@ from ek_emulator import Emulator, Unsupported
 import test_gpu_fuzz as fuzz
 
 
+@pytest.fixture(autouse=True, params=["assembled", "lowered"])
+def program_form(request):
+    """Every test of this module runs twice: on the assembler's program and on the program lowered for the 32-bit fast
+    kernel (ek_eval.cpp lower_fast -> ek_sweep_fast.cu), raised back by ek_emulator.raise_fast."""
+    Emulator.prefer_fast = request.param == "lowered"
+    yield request.param
+    Emulator.prefer_fast = False
+
+
 class _Factory:
     """Stands in for Float32.copy / UInt32.copy: a fake device mapping plus the data the emulator reads."""
     def __init__(self, cls, table, base):
@@ -438,3 +447,39 @@ def test_simplified_edge_weights_on_the_emulator(ek, oracle, P):
     assert ek.debug_plan() == ""
     _case_simplified_weights(ek, oracle, P)
     gc.collect()
+
+
+def test_side_effects_run_in_recording_order(ek, oracle, P):
+    """roots were planned by descending handle, so of two scatters into the same target the one
+    recorded FIRST won.  The reference walks monotonically increasing ids (jit.cu:1385-1416): the later one wins, and a
+    scatter_add recorded after a scatter adds to the scattered value.  Handles are recycled here (LIFO free list), so the
+    test also churns the handle table first to make handle order differ from creation order."""
+    import gc
+    from enoki_b200 import Float32, UInt32, scatter, scatter_add
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    n, m = 1000, 64
+    rng = np.random.default_rng(7)
+    for churn in range(2):
+        junk = [Float32(float(k)) for k in range(5 + 3 * churn)]       # allocate, then free in an order that scrambles the free list
+        del junk[::2]; del junk
+        table = {}
+        F = _Factory(Float32, table, 0x7f0000000000); U = _Factory(UInt32, table, 0x7a0000000000)
+        a_n, b_n = rng.uniform(-1, 1, n).astype(np.float32), rng.uniform(-1, 1, n).astype(np.float32)
+        i_n = rng.integers(0, m, n).astype(np.uint32)
+        t1_n = np.zeros(m, np.float32); t2_n = np.zeros(m, np.float32)
+        a, b, idx = F.copy(a_n), F.copy(b_n), U.copy(i_n)
+        t1, t2 = F.copy(t1_n), F.copy(t2_n)
+        scatter(t1, a * 2.0, idx)                   # recorded first
+        scatter(t1, b * 3.0, idx)                   # recorded second: must win wherever both write
+        scatter(t2, a, idx)
+        scatter_add(t2, b, idx)                     # must see the scattered values
+        emu = Emulator(oracle, table, _Factory.addresses)
+        emu.run(ek.debug_program())
+        want1 = t1_n.copy(); want1[i_n] = (a_n * np.float32(2.0)); want1[i_n] = (b_n * np.float32(3.0))
+        assert (emu.vars[t1.index].view(np.uint32) == want1.view(np.uint32)).all()
+        want2 = t2_n.copy(); want2[i_n] = a_n
+        acc = want2.astype(np.float64); np.add.at(acc, i_n, b_n.astype(np.float64))
+        assert np.allclose(emu.vars[t2.index], acc, rtol=1e-5, atol=1e-6)
+        ek.lib().ek_debug_discard_side_effects()
+        del a, b, idx, t1, t2
+        gc.collect()

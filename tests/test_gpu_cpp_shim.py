@@ -43,8 +43,6 @@ def test_cpp_autodiff_parity(gpu):
     assert "all checks passed" in r.stdout
 
 
-@pytest.mark.skipif(os.environ.get("EK_ENABLE_PARTITION") is None,
-                    reason="virtual-call dispatch is unverified in round 1 (see ek_partition); opt in with EK_ENABLE_PARTITION=1")
 @pytest.mark.parametrize("n", ["1000", "100003", "4194304"])
 def test_cpp_virtual_call_dispatch(gpu, n):
     """SURVEY 8f row 1: ENOKI_CALL_SUPPORT dispatch through CUDAArray<T *>::partition_() -> ek_partition, compared bit

@@ -426,8 +426,6 @@ def test_psum_compress_raw(gpu):
     assert (got == u[mask]).all()
 
 
-@pytest.mark.skipif(os.environ.get("EK_ENABLE_PARTITION") is None,
-                    reason="ek_partition is unverified in round 1 (two GPU boxes were lost on its first runs); opt in with EK_ENABLE_PARTITION=1")
 @pytest.mark.parametrize("n,k", [(1, 1), (31, 3), (100_003, 7), (1 << 22, 40), (50_000, 1500)])
 def test_partition(gpu, n, k):
     """cuda_partition (horiz.cu:35-122) feeds virtual-call dispatch: groups of indices per distinct pointer, pointers
