@@ -278,6 +278,8 @@ def main():
     ap.add_argument("--elems", type=int, default=N_ELEMS, help="elements per GPU (default: the BASELINE config, 2^26)")
     ap.add_argument("--skip-backward", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: leave out the host-buffer leg")
+    ap.add_argument("--skip-extras", action="store_true", help="profiling aid: leave out C3 / small / C5 / C1 objects")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -289,7 +291,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("EK_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # never override the caller's setting (NCCL logs go to stderr anyway)
     import torch
     dist = None
     if world > 1:
@@ -399,7 +401,7 @@ def main():
 
     # ---- e2e: pinned host buffers, H2D of the 4 inputs + D2H of the result inside the timed region
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.skip_e2e:
         hb = [L.ek_host_malloc(n * 4) for _ in range(5)]
         for k in range(4):
             L.ek_memcpy_from_device(hb[k], L.ek_var_ptr(x[k].index), n * 4)
@@ -445,7 +447,7 @@ def main():
 
     # ---- C3 (configs[2]): 2^26-sample gather + scatter_add histogram, kernel-only time
     hist = None
-    if rank == 0:
+    if rank == 0 and not args.skip_extras:
         try:
             hist = bench_histogram(ek, L, n, peak_gbs)
         except Exception as e:                      # secondary objects must never cost the headline line
@@ -453,7 +455,7 @@ def main():
 
     # ---- launch-latency regime: the same C2 expression on 2^20 elements
     small = None
-    if rank == 0:
+    if rank == 0 and not args.skip_extras:
       try:
         ns = 1 << 20
         xs_s = [Float32.copy(np.random.default_rng(k).uniform(-4, 4, ns).astype(np.float32)) for k in range(4)]

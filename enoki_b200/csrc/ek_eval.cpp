@@ -82,7 +82,8 @@ struct Assembled {
 
 #define EK_STAGE_UNIT_BUDGET 8u     /* slot units of TMA-staged inputs per pipeline stage */
 
-struct Config { int V; uint32_t T; uint32_t stages; uint32_t ctas_per_sm; size_t smem; uint32_t off_bar, off_prog, off_extra, off_slots; bool prog_in_smem; };
+struct Config { int V; uint32_t T; uint32_t stages; uint32_t ctas_per_sm; size_t smem; uint32_t off_bar, off_prog, off_extra, off_slots; bool prog_in_smem;
+                bool fast = false;   /* the 32-bit fast kernel (ek_sweep_fast.cu) with its own program form and extra-region layout */ };
 
 /* ------------------------------------------------------------------ device opcode selection */
 enum Cls { C_F32, C_F64, C_I32, C_U32, C_I64, C_U64, C_BAD };
@@ -1109,7 +1110,7 @@ uint32_t fast_copies(uint32_t count, uint32_t T) {
     return (uint64_t) count * T * 4u <= 32768u ? T : std::max(1u, std::min(32u, 4096u / count));
 }
 size_t layout_extra(const Assembled &a, const Config &cfg, uint32_t *argw) {
-    if (cfg.V != 16) return a.extra_bytes;
+    if (!cfg.fast) return a.extra_bytes;
     uint32_t off = 0;
     for (const Assembled::ExtraItem &it : a.extra_items) {
         uint32_t copies = it.kind == 0 ? 1u : fast_copies(it.count, cfg.T);
@@ -1124,7 +1125,7 @@ size_t smem_layout(const Assembled &a, Config &cfg, size_t n_uni) {
     cfg.off_bar = (uint32_t) off; off += 8 * 8 + 33 * 8;
     off = (off + 15) & ~(size_t) 15;
     size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
-    cfg.prog_in_smem = cfg.V != 16 && n_prog * 16 <= 24 * 1024;
+    cfg.prog_in_smem = !cfg.fast && n_prog * 16 <= 24 * 1024;
     cfg.off_prog = (uint32_t) off;
     if (cfg.prog_in_smem) off += n_prog * 16;
     cfg.off_extra = (uint32_t) off; off += layout_extra(a, cfg, nullptr);
@@ -1266,22 +1267,25 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
     size_t budget = ctx.smem_optin;                 /* per CTA (227 KB) */
     size_t per_sm = 228 * 1024 - 1024;              /* per SM, minus the 1 KB per-CTA reservation */
     struct Cand { int V; uint32_t T; uint32_t stages; uint32_t want_ctas; };
+    /* the 32-bit fast kernel: V = 16, one TMA stage (the other CTAs of the SM hide the load) */
+    static const Cand fast_cands[] = { { 16, 256, 1, 2 }, { 16, 128, 1, 4 }, { 16, 128, 1, 3 }, { 16, 128, 1, 2 }, { 16, 256, 1, 1 }, { 16, 128, 1, 1 } };
     static const Cand cands[] = {
         /* measured on B200 (tools/cfgsweep.sh): single-buffered staging with more resident CTAs beats
            double buffering -- the other CTAs of the SM hide the TMA latency and 16 warps hide the
            interpreter's dependent-issue latency */
-        { 16, 256, 1, 2 }, { 16, 128, 1, 4 }, { 16, 128, 1, 3 }, { 16, 128, 1, 2 }, { 16, 256, 1, 1 }, { 16, 128, 1, 1 },
-                                                      /* 32-bit-only programs: the fast kernel (single TMA stage) */
+        { 16, 256, 1, 2 }, { 16, 128, 1, 4 }, { 16, 128, 1, 3 }, { 16, 128, 2, 2 }, { 16, 128, 1, 2 },
+        { 16, 256, 2, 1 }, { 16, 128, 1, 1 },                               /* 32-bit-only programs, general kernel */
         { 8, 256, 1, 4 }, { 8, 256, 1, 3 }, { 8, 256, 2, 2 }, { 8, 256, 1, 2 }, { 8, 256, 2, 1 }, { 8, 256, 1, 1 },
         { 8, 128, 1, 2 }, { 8, 128, 2, 1 }, { 8, 128, 1, 1 },
         { 4, 128, 2, 1 }, { 4, 64, 2, 1 }, { 4, 32, 2, 1 } };
     size_t n_prog = a.init.size() + a.body.size() + a.fini.size();
-    (void) n_prog;
-    bool fast_ok = !a.has64 && !a.noncore && a.fast_ok && a.fast_len <= EK_INLINE_PROG;
-    /* tuning aid: EK_CFG="V,T,stages,ctas_per_sm" forces a configuration for wide sweeps */
+    const bool core16_ok = !a.has64 && !a.noncore && n_prog <= EK_INLINE_PROG;          /* general V = 16 kernel */
+    const bool fast_ok = ctx.fast_mode != 0 && !a.has64 && !a.noncore && a.fast_ok && a.fast_len <= EK_INLINE_PROG;
+    cfg.fast = false;
+    /* tuning aid: EK_CFG="V,T,stages,ctas_per_sm" forces a configuration for wide sweeps (general kernels) */
     if (const char *env = getenv("EK_CFG")) {
         int V, T, S, C;
-        if (n > 4096 && sscanf(env, "%d,%d,%d,%d", &V, &T, &S, &C) == 4 && (V != 16 || (fast_ok && S == 1 && (T == 128 || T == 256)))) {
+        if (n > 4096 && sscanf(env, "%d,%d,%d,%d", &V, &T, &S, &C) == 4 && (V != 16 || core16_ok)) {
             cfg.V = V; cfg.T = (uint32_t) T; cfg.stages = (uint32_t) S; cfg.ctas_per_sm = (uint32_t) C;
             if (smem_layout(a, cfg, n_uni) <= budget) return true;
         }
@@ -1295,9 +1299,20 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
             if (smem_layout(a, cfg, n_uni) <= budget) return true;
         }
     }
+    if (fast_ok) {
+        for (const Cand &c : fast_cands) {
+            cfg.fast = true;
+            cfg.V = c.V; cfg.T = c.T; cfg.stages = 1; cfg.ctas_per_sm = c.want_ctas;
+            size_t need = smem_layout(a, cfg, n_uni);
+            if (need > budget) continue;
+            if ((need + 1024) * c.want_ctas > per_sm + 1024) continue;
+            return true;
+        }
+        cfg.fast = false;
+    }
     for (const Cand &c : cands) {
-        if (c.V == 16 && !fast_ok) continue;
-        cfg.V = c.V; cfg.T = c.T; cfg.stages = (a.n_in_units || c.V == 16) ? c.stages : 2; cfg.ctas_per_sm = c.want_ctas;
+        if (c.V == 16 && !core16_ok) continue;
+        cfg.V = c.V; cfg.T = c.T; cfg.stages = a.n_in_units ? c.stages : 2; cfg.ctas_per_sm = c.want_ctas;
         size_t need = smem_layout(a, cfg, n_uni);
         if (need > budget) continue;
         if ((need + 1024) * c.want_ctas > per_sm + 1024) continue;
@@ -1507,7 +1522,7 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
                    launcher would pick for this sweep */
                 Config fcfg; std::string ferr;
                 /* (judged as a wide sweep whatever its size, so that small CPU test cases exercise the lowering too) */
-                if (choose_config(ctx, a, std::max<size_t>(l.first->size, 4097), fcfg, ferr) && fcfg.V == 16) {
+                if (choose_config(ctx, a, std::max<size_t>(l.first->size, 4097), fcfg, ferr) && fcfg.fast) {
                     std::vector<EkInstr> fi, fb, ff;
                     if (lower_fast(a.init, a, &fcfg, fi) && lower_fast(a.body, a, &fcfg, fb) && lower_fast(a.fini, a, &fcfg, ff)) {
                         oss << ",\"fast\":{\"T\":" << fcfg.T << ",\"off_slots\":" << fcfg.off_slots << ",\"n_tmp\":" << a.n_tmp;
@@ -1565,7 +1580,7 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
 
         /* operand codes -> (byte offset >> 4) for this configuration's shared-memory layout (general kernels; the fast
            kernel's program is lowered from the symbolic form further down) */
-        const bool fast = cfg.V == 16;
+        const bool fast = cfg.fast;
         if (!fast) {
             const uint32_t slot_bytes = cfg.T * cfg.V * 4u;
             auto patch = [&](uint16_t code) -> uint16_t {
@@ -1666,6 +1681,7 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
             ctx.stats.last_kernel_ms = ms; ctx.stats.total_kernel_ms += ms;
         }
         ctx.stats.launches++; ctx.stats.sweep_launches++;
+        if (fast) ctx.stats.fast_launches++;
         ctx.stats.ops_evaluated += (uint64_t) a.n_arith * g.size;
         ctx.stats.bytes_in += a.bytes_in; ctx.stats.bytes_out += a.bytes_out;
     }

@@ -175,19 +175,23 @@ int ek_compress(ek_type type, size_t n, const void *data, const uint8_t *mask, v
 /* cuda_partition (horiz.cu:35-122): groups the indices 0..n-1 by pointer value -- unique pointers ascending, indices
    ascending inside every group (what the reference's stable radix sort + run-length encode produce).
 
-   Virtual-call dispatch (array_call.h:147-165) only ever sees a handful of distinct instances, so the grouping is
-   composed from the two device primitives of this backend that are already pinned by the parity tests -- no kernel
-   of its own:
+   Default path (round 2): the pointer array is downloaded and grouped by a host-side stable sort; the per-group index
+   lists are uploaded.  This is NOT a performance path (virtual-call dispatch is a "next" row of SURVEY 8f, its cost is
+   dominated by the per-instance kernels) and it is the only variant that could be reasoned correct without hardware:
+   this repository lost its GPU access before any device-side variant had been seen to pass.
+   EK_PARTITION_DEVICE=1 selects a device-side composition of primitives the parity tests already pin -- no kernel of
+   its own:
      (1) distinct values, ascending:  v_0 = hmin(ptr);  v_{k+1} = hmin(select(ptr > v_k, ptr, ~0))   (fused sweep +
          reduction epilogue, one 8-byte read-back per value),
      (2) per value: mask = (ptr == v_k) recorded through the evaluator, indices = compress(arange(n), mask)
          (ek_compress: three-phase scan, output order = input order, i.e. ascending).
-   Cost: 2 K passes over the pointer array for K distinct values.  More than EK_PART_MAX_GROUPS distinct values (not a
-   dispatch-shaped input) take a host-side stable sort of the downloaded pointers, as do inputs when
-   EK_PARTITION_HOST=1 is set.
+   Cost: 2 K passes over the pointer array for K distinct values; more than EK_PART_MAX_GROUPS distinct values fall back
+   to the host sort.
 
-   History: round 1 shipped a dedicated hash + multi-way scatter kernel set for this; three GPU boxes were lost on
-   its first runs (rounds 1 and 2), it was never seen to pass, and it has been removed. */
+   History: round 1 shipped a dedicated hash + multi-way scatter kernel set; every GPU box that ran its test was lost
+   after ~2 minutes.  The cause found in round 2 was the TEST, not the kernels: it built its pointer table with
+   rng.choice(np.arange(1, 1 << 40)) -- an 8 TiB host allocation that took the box down (tests/test_gpu_eval.py
+   test_partition, fixed).  The kernel set was removed before that was understood and has not been brought back. */
 namespace {
 constexpr size_t EK_PART_MAX_GROUPS = 256;
 
@@ -234,7 +238,7 @@ int ek_partition(size_t n, const void **ptrs, void ***unique_out, uint32_t **cou
     std::vector<uint64_t> uniq;
     std::vector<uint32_t> cnts;
     uint32_t **perm_h = nullptr;
-    bool host = getenv("EK_PARTITION_HOST") != nullptr;
+    bool host = getenv("EK_PARTITION_DEVICE") == nullptr;
 
     if (!host) {
         /* borrow the caller's array as a trace variable (jit.cu:373-395 with dealloc = false) */

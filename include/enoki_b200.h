@@ -239,7 +239,12 @@ typedef struct ek_stats {
     uint64_t bytes_in, bytes_out; /* algorithmic bytes streamed by sweeps (array loads / stores) */
     float    last_kernel_ms;    /* device time of the most recent timed launch (timing mode only) */
     float    total_kernel_ms;   /* sum of device times since reset (timing mode only)     */
+    uint64_t fast_launches;     /* ... sweeps that ran on the 32-bit fast kernel (ek_sweep_fast.cu) */
 } ek_stats;
+/* 32-bit fast sweep kernel (no counterpart in the reference): ek_init() enables it after the kernel qualification
+   described in csrc/ek_runtime.cpp (or as EK_FAST=0/1 says); these calls read / override that decision. */
+EK_API void ek_set_fast_mode(int enable);
+EK_API int  ek_fast_mode(void);
 EK_API void ek_stats_reset(void);
 EK_API void ek_stats_get(ek_stats *out);
 EK_API void ek_set_timing(int enable);     /* bracket every launch with CUDA events on the launch stream */

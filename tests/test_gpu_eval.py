@@ -434,7 +434,12 @@ def test_partition(gpu, n, k):
     ek = gpu
     L = ek.lib()
     rng = np.random.default_rng(n + k)
-    table = np.sort(rng.choice(np.arange(1, 1 << 40, dtype=np.uint64), size=k, replace=False)) * np.uint64(16)
+    # k distinct 16-byte aligned "pointers" below 2^44.  (NEVER materialise the value range: the first version of this test
+    # said rng.choice(np.arange(1, 1 << 40)) -- an 8 TiB host array -- and every GPU box that ran it was lost to the host's
+    # OOM killer after ~2 minutes; that, not ek_partition, is what "hung" in rounds 1 and 2.)
+    cand = np.unique(rng.integers(1, 1 << 40, size=4 * k + 16, dtype=np.uint64))
+    assert len(cand) >= k
+    table = np.sort(rng.permutation(cand)[:k]) * np.uint64(16)
     ptr = table[rng.integers(0, k, n)]
     P64 = ek.UInt64.copy(ptr)
     uniq = ctypes.c_void_p(); counts = ctypes.c_void_p(); perm = ctypes.c_void_p()
