@@ -1525,7 +1525,15 @@ static int eval_impl(bool dry, std::string *dump, bool json = false) {
                 if (choose_config(ctx, a, std::max<size_t>(l.first->size, 4097), fcfg, ferr) && fcfg.fast) {
                     std::vector<EkInstr> fi, fb, ff;
                     if (lower_fast(a.init, a, &fcfg, fi) && lower_fast(a.body, a, &fcfg, fb) && lower_fast(a.fini, a, &fcfg, ff)) {
-                        oss << ",\"fast\":{\"T\":" << fcfg.T << ",\"off_slots\":" << fcfg.off_slots << ",\"n_tmp\":" << a.n_tmp;
+                        oss << ",\"fast\":{\"T\":" << fcfg.T << ",\"off_slots\":" << fcfg.off_slots << ",\"n_tmp\":" << a.n_tmp
+                            << ",\"off_bar\":" << fcfg.off_bar << ",\"off_extra\":" << fcfg.off_extra << ",\"smem\":" << fcfg.smem
+                            << ",\"n_in_units\":" << a.n_in_units << ",\"n_red\":" << a.n_red << ",\"argw\":[";
+                        {   /* argument words with the fast kernel's extra-region layout (pointer words still unpatched) */
+                            std::vector<uint32_t> aw(a.argw);
+                            layout_extra(a, fcfg, aw.data());
+                            for (size_t i = 0; i < aw.size(); ++i) oss << (i ? "," : "") << aw[i];
+                        }
+                        oss << "]";
                         auto fsec = [&](const char *name, const std::vector<EkInstr> &v) {
                             oss << ",\"" << name << "\":[";
                             /* (fop, fflags, b, c, dst, aux, imm): see the field shuffle in lower_fast */

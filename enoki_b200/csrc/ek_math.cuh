@@ -12,7 +12,9 @@
  */
 #pragma once
 #include <stdint.h>
+#ifndef EK_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 
 namespace ekm {
 
@@ -129,6 +131,9 @@ __device__ __forceinline__ float log_f32(float x) {
    tools/micro/f32x2.cu -- which would change the rounding.) */
 struct f2 { float x, y; };
 __device__ __forceinline__ f2 mk2(float v) { return f2{ v, v }; }
+#ifdef EK_HOST_EMU          /* tests/cpu_kernel: both halves round like the scalar fma */
+__device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { return f2{ fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y) }; }
+#else
 __device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) {
     f2 r;
     asm("{\n .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
@@ -136,6 +141,7 @@ __device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) {
         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return r;
 }
+#endif
 __device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return ffma2(a, b, mk2(-0.f)); }
 __device__ __forceinline__ f2 fadd2(f2 a, f2 b) { return ffma2(a, mk2(1.f), b); }
 __device__ __forceinline__ f2 fsub2(f2 a, f2 b) { return ffma2(b, mk2(-1.f), a); }

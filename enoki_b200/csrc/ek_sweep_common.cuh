@@ -4,13 +4,50 @@
  * the generic reduction combine, warp-aggregated global atomics.
  */
 #pragma once
+#ifndef EK_HOST_EMU          /* tests/cpu_kernel: the fast kernel compiled as host code, see cuda_shim.h */
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "ek_isa.h"
 #include "ek_math.cuh"
 
 namespace {
 
+#ifdef EK_HOST_EMU
+/* host emulation (tests/cpu_kernel): shared-space addresses are offsets into the CTA's buffer, an mbarrier is a word
+   {bit 0: parity of the current phase, bits 32..: pending transaction bytes}, a TMA bulk copy is a memcpy */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+inline uint8_t *emu_smem_ptr(uint32_t addr) { return emu::smem_ + (addr - emu::SMEM_WINDOW); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t) bytes << 32, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t) bytes << 32, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
+    const uint64_t w = __atomic_load_n(reinterpret_cast<uint64_t *>(emu_smem_ptr(bar_addr)), __ATOMIC_SEQ_CST);
+    return ((uint32_t) w & 1u) != parity;
+}
+__device__ __forceinline__ void mbar_wait_watchdog(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (unsigned long spins = 0; !mbar_try_wait(a, parity); ++spins) { if (spins > 200000000ul) emu::trap("mbarrier never completed"); sched_yield(); }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { mbar_wait_watchdog(bar, parity); }
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    if (((uintptr_t) src & 15u) || (bytes & 15u) || (smem_u32(dst_smem) & 15u)) emu::trap("misaligned bulk copy");
+    memcpy(dst_smem, src, bytes);
+    const uint64_t left = __atomic_sub_fetch(bar, (uint64_t) bytes << 32, __ATOMIC_SEQ_CST);
+    if ((left >> 32) == 0) __atomic_fetch_xor(bar, 1ull, __ATOMIC_SEQ_CST);       /* phase complete */
+}
+__device__ __forceinline__ void tma_prefetch_l2(const void *, uint32_t) {}
+__device__ __forceinline__ void fence_barrier_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    if (addr & 15u) emu::trap("misaligned 128-bit shared load");
+    return *reinterpret_cast<const uint4 *>(emu_smem_ptr(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    if (addr & 15u) emu::trap("misaligned 128-bit shared store");
+    *reinterpret_cast<uint4 *>(emu_smem_ptr(addr)) = v;
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t) __cvta_generic_to_shared(p);
 }
@@ -83,6 +120,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+#endif
 /* value the compiler must keep in a register (no rematerialisation, no hoisting across this point) */
 __device__ __forceinline__ uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 
