@@ -228,6 +228,9 @@ struct Assembler {
     std::vector<uint8_t> slot_used;
     std::unordered_map<uint32_t, uint32_t> red_acc;    /* reduce var -> accumulator slot */
     std::unordered_set<uint32_t> direct;               /* wide inputs loaded with ld.global instead of TMA staging */
+    std::unordered_set<uint32_t> implied_mask;         /* gathers / scatter_adds whose mask is implied by the range check of
+                                                          their shared-memory table / bins (see mask_is_implied) */
+    std::unordered_set<uint32_t> dead;                 /* mask variables that only fed such operations: not emitted */
     uint32_t acc_var = 0;
     uint32_t cur_e = 0;
 
@@ -366,8 +369,64 @@ struct Assembler {
     }
     bool boundary_input(uint32_t idx) const { return g.boundary.count(idx) != 0; }
 
+    /* does this gather / scatter_add go through a table / privatised bins in shared memory? (the same tests as in
+       emit_var) -- count = number of entries */
+    bool uses_smem(const EkVariable &v, uint32_t &count) const {
+        if (!wide() || v.extra_dep < EK_REG_RESERVED) return false;
+        const EkVariable &pv = var(v.dep[0]), &tv = var(v.extra_dep);
+        ek_type it = var(v.dep[1]).type;
+        if (ek_is_64(it) || ek_is_signed(it) || tv.data != pv.data || ek_type_size(tv.type) != 4) return false;
+        count = (uint32_t) tv.size;
+        if (v.op == EK_OP_GATHER) {
+            uint32_t stride = (uint32_t) (v.imm & 0x7fffu);
+            return (stride == 0 || stride == 4) && ek_type_size(v.type) == 4 && !ek_is_64(v.type) && tv.size <= 4096;
+        }
+        if (v.op == EK_OP_SCATTER_ADD) {
+            ek_type vt = var(v.dep[3]).type;
+            uint32_t stride = (uint32_t) ((v.imm >> 32) & 0x7fffu);
+            return ek_type_size(vt) == 4 && (stride == 0 || stride == 4) && tv.size <= 1024;
+        }
+        return false;
+    }
+    /* The shared-memory forms test `index < count` themselves.  A mask that is exactly `index < L` with a literal
+       L >= count (the histogram idiom: idx < n_bins) adds nothing: the operation is given a literal-true mask, and if the
+       comparison has no other use it is not computed at all (one dispatch and one slot less per tile). */
+    bool mask_is_implied(const EkVariable &v) const {
+        uint32_t count = 0;
+        if ((v.op != EK_OP_GATHER && v.op != EK_OP_SCATTER_ADD) || !uses_smem(v, count)) return false;
+        uint32_t m = v.dep[2];
+        if (m < EK_REG_RESERVED) return false;
+        const EkVariable &mv = var(m);
+        if (mv.data != nullptr || mv.op != EK_OP_LT || mv.dep[0] != v.dep[1] || mv.size != v.size) return false;
+        if (boundary_input(m)) return false;
+        const EkVariable &lv = var(mv.dep[1]);
+        if (lv.op != EK_OP_LITERAL || lv.data != nullptr || ek_is_64(lv.type) || ek_is_signed(var(mv.dep[0]).type) || ek_is_float(var(mv.dep[0]).type)) return false;
+        return (uint32_t) lv.imm >= count;
+    }
+
     bool run() {
-        /* ---- pass 0: wide inputs beyond the staging budget are loaded directly (ld.global) ---- */
+        /* ---- pass 0: masks implied by the range check of a shared-memory table / bins ---- */
+        {
+            std::unordered_map<uint32_t, int> other_uses;
+            for (uint32_t idx : g.sched) {
+                const EkVariable &v = var(idx);
+                if (v.data != nullptr || v.direct_pointer || boundary_input(idx) || v.op == EK_OP_LITERAL) continue;
+                const bool implied = mask_is_implied(v);
+                if (implied) implied_mask.insert(idx);
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t d = v.dep[k];
+                    if (d < EK_REG_RESERVED) continue;
+                    if (!(implied && k == 2)) other_uses[d]++;
+                }
+            }
+            for (uint32_t idx : implied_mask) {
+                uint32_t m = var(idx).dep[2];
+                const EkVariable &mv = var(m);
+                if (other_uses[m] == 0 && mv.ref_ext == 0 && !mv.side_effect && !forced.count(m) && g.visited.count(m) &&
+                    std::find(g.roots.begin(), g.roots.end(), m) == g.roots.end()) dead.insert(m);
+            }
+        }
+        /* ---- pass 0b: wide inputs beyond the staging budget are loaded directly (ld.global) ---- */
         {
             uint32_t units = 0, count = 0;
             for (uint32_t idx : g.sched) {
@@ -396,7 +455,7 @@ struct Assembler {
             bool emitting;
             if (is_input) emitting = direct.count(idx) != 0;
             else if (v.op == EK_OP_LITERAL) emitting = lit_emits(idx);
-            else emitting = true;
+            else emitting = dead.count(idx) == 0;
             if (emitting) {
                 ++e;
                 bool computes = !is_input && v.op != EK_OP_LITERAL;
@@ -406,6 +465,7 @@ struct Assembler {
                     for (int k = 0; k < 4; ++k) {
                         uint32_t d = v.dep[k];
                         if (d < EK_REG_RESERVED) continue;
+                        if (k == 2 && implied_mask.count(idx)) continue;        /* (that operand is not read) */
                         last_use[d] = (uint32_t) i;
                         last_epos[d] = e;
                         if (d == prev_emitted) { prev_used = true; if (k < 3 && (accp >> k) & 1u) prev_ok = true; }
@@ -513,6 +573,7 @@ struct Assembler {
             }
             if (v.data != nullptr || v.direct_pointer || boundary_input(idx)) continue;
             if (v.op == EK_OP_LITERAL && !lit_emits(idx)) continue;
+            if (dead.count(idx)) continue;
             cur_e = emits[i];
             if (!emit_var(idx, (uint32_t) i)) return false;
         }
@@ -652,7 +713,10 @@ struct Assembler {
                     in = mk(dop, (sgn ? 0x80000000u : 0u) | (stride << 16) | pa);
                     set_mark(in, 3);         /* marker: imm low 16 bits hold a uniform code to rebase */
                 }
-                put_b(in, d2);
+                if (implied_mask.count(idx)) {
+                    if (!smem_table) return fail("internal: implied mask on a gather without a shared-memory table");
+                    set_b_code(in, uni_lit(lit_word(1u)), false);
+                } else put_b(in, d2);
                 if (ek_is_64(it)) in.flags |= EKF_A64;
             } break;
             case EK_OP_SCATTER: case EK_OP_SCATTER_ADD: {
@@ -701,7 +765,10 @@ struct Assembler {
                     set_mark(in, 3);
                 }
                 put_b(in, d3);
-                put_c(in, d2);
+                if (implied_mask.count(idx)) {
+                    if (!smem_bins) return fail("internal: implied mask on a scatter_add without privatised bins");
+                    set_c_code(in, uni_lit(lit_word(1u)), false);
+                } else put_c(in, d2);
                 if (ek_is_64(it)) in.flags |= EKF_A64;
                 produces = false;
             } break;
@@ -1194,10 +1261,13 @@ bool lower_fast(const std::vector<EkInstr> &in, const Assembled &a, const Config
             if (is_uni(i.a)) emit(FOP_LOADU, 0, enc(i.a), 0, 0, 0, 0);
             else emit(FOP_LOAD, 0, enc(i.a), 0, 0, 0, 0);
         }
-        if (i.flags & EKF_ABS_A) emit(FOP_ABS_F32, 0, 0, 0, 0, 0, 0);
-        if (i.flags & EKF_NEG_A) emit(FOP_NEG_F32, 0, 0, 0, 0, 0, 0);
+        /* (|x| is applied before -x, like the general kernel does; exp(-x) and sqrt(|x|) have fused forms) */
+        const bool fuse_neg = i.op == DOP_EXP_F32 && (i.flags & EKF_NEG_A) && !(i.flags & EKF_ABS_A);
+        const bool fuse_abs = i.op == DOP_SQRT_F32 && (i.flags & EKF_ABS_A) && !(i.flags & EKF_NEG_A);
+        if ((i.flags & EKF_ABS_A) && !fuse_abs) emit(FOP_ABS_F32, 0, 0, 0, 0, 0, 0);
+        if ((i.flags & EKF_NEG_A) && !fuse_neg) emit(FOP_NEG_F32, 0, 0, 0, 0, 0, 0);
         /* 2. the operation */
-        int fop = fop_of(i.op);
+        int fop = fuse_neg ? FOP_EXPN_F32 : fuse_abs ? FOP_SQRTA_F32 : fop_of(i.op);
         if (fop < 0) return false;
         uint32_t fl = 0;
         uint16_t b = 0, c = 0, dst = 0, aux = 0;

@@ -170,6 +170,7 @@ enum EkDop : uint16_t {
     X(FMA_F32) X(FMA_F32_UB) X(FMA_F32_UC) X(FMAC_F32) X(FMAC_F32_UB) \
     X(MAD_I32) X(MADC_I32) X(FMANZ_F32) X(FMANZC_F32) X(SEL_M_32) X(SEL_T_32) X(SEL_F_32) \
     X(ABS_F32) X(NEG_F32) X(SQRT_F32) X(RCP_F32) X(RSQRT_F32) X(EXP_F32) X(LOG_F32) X(SIN_F32) X(COS_F32) \
+    X(EXPN_F32) X(SQRTA_F32)   /* exp(-x), sqrt(|x|): the input modifier folded into the operation */ \
     X(FLOOR_F32) X(CEIL_F32) X(ROUND_F32) X(TRUNC_F32) X(ABS_I32) X(NEG_I32) X(NOT_32) X(NOT_B) X(NEZ_32) \
     X(CVT_F32_I32) X(CVT_F32_U32) X(CVT_I32_F32) X(CVT_U32_F32) \
     X(LOAD) X(LOADU) X(INDEX) X(LD_U8) X(LD_S8) X(LDG_32) X(ST_32) X(ST_8) \

@@ -51,6 +51,9 @@ def raise_fast(fast, fop_names, op_index):
         if fl & FF_CU: flags |= F_HAS_C; cc = uni(c)
         if name in ("LOAD", "LOADU"):
             flags |= F_HAS_B; cb = slot(b) if name == "LOAD" else uni(b); name = "LOAD_32"
+        elif name in ("EXPN_F32", "SQRTA_F32"):
+            flags |= F_NEG_A if name == "EXPN_F32" else F_ABS_A
+            name = "EXP_F32" if name == "EXPN_F32" else "SQRT_F32"
         elif name.endswith("_U") and name[:-2] in op_index:
             flags |= F_HAS_B; cb = uni(b); name = name[:-2]
         elif name == "FMA_F32_UB": flags |= F_HAS_B; cb = uni(b); name = "FMA_F32"
