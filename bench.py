@@ -320,6 +320,16 @@ def main():
     ek.cuda_eval(); ek.cuda_sync()
     del idx
 
+    native_nccl = False
+    # EK_BENCH_NATIVE_NCCL=1: the per-step all-reduce through the library's own communicator (C ABI, csrc/ek_dist.cpp).
+    # Off by default in round 2: that path has not run on hardware yet, the torch.distributed one has (round 1, N=2).
+    if world > 1 and os.environ.get("EK_BENCH_NATIVE_NCCL") == "1":
+        try:
+            from enoki_b200.dist import init_native
+            native_nccl = init_native(rank, world, torch.device("cuda", local_rank))
+        except Exception as e:
+            print(f"bench.py: native NCCL path unavailable: {e!r}", file=sys.stderr)
+
     class DevScalar:
         """expose a 4-byte device buffer to torch (NCCL all-reduce of the loss scalar)"""
         def __init__(self, ptr):
@@ -334,8 +344,12 @@ def main():
         s = hsum(out) if reduce_scalar else None
         ek.cuda_eval()
         if world > 1 and s is not None:
-            from enoki_b200.dist import allreduce_device_scalar
-            allreduce_device_scalar(L.ek_var_ptr(s.index), "f32", L.ek_stream(), torch.device("cuda", local_rank))
+            if native_nccl:         # one ncclAllReduce enqueued by the library on its own stream (csrc/ek_dist.cpp)
+                from enoki_b200.dist import allreduce_handles
+                allreduce_handles([s])
+            else:                   # round-1 path: torch.distributed on the backend's stream
+                from enoki_b200.dist import allreduce_device_scalar
+                allreduce_device_scalar(L.ek_var_ptr(s.index), "f32", L.ek_stream(), torch.device("cuda", local_rank))
         return out, s
 
     def barrier():
@@ -391,12 +405,25 @@ def main():
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     achieved = C2_BYTES_PER_ELEM * n / (kern_ms * 1e-3) / 1e9
+    on_fast = int(stt.fast_launches) > 0         # which sweep kernel really ran (ek_init's kernel qualification decides)
+    traffic, traffic_src = None, None
+    if not on_fast and n == (1 << 26):
+        # DRAM bytes of one launch of the general kernel from the committed `ncu --set full` capture of this workload
+        try:
+            traffic_src = "profiles/r1_final_sweep_ncu_summary.txt"
+            txt = open(os.path.join(ROOT, traffic_src)).read()
+            import re
+            rd = re.search(r"dram__bytes_read\.sum \[(\w+)\] = ([0-9.]+)", txt); wr = re.search(r"dram__bytes_write\.sum \[(\w+)\] = ([0-9.]+)", txt)
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            traffic = float(rd.group(2)) * unit[rd.group(1)] + float(wr.group(2)) * unit[wr.group(1)]
+        except Exception:
+            traffic, traffic_src = None, None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
-                # (profiles/r1_v8a_sweep_ncu_summary.txt: dram__bytes_read.sum 1.074 GB + dram__bytes_write.sum 0.249 GB)
-                "traffic": 1.323e9 if n == (1 << 26) else None, "traffic_unit": "B/launch",
+                "traffic": traffic, "traffic_unit": "B/launch", "traffic_source": traffic_src if traffic is not None else
+                "none: no ncu capture of ek_fast_kernel exists (the repository had no GPU access after the kernel was written)",
                 "algorithmic_bytes": C2_BYTES_PER_ELEM * n,
-                "kernel": "ek_sweep_kernel<16,false,true>", "kernel_ms": kern_ms,
+                "kernel": "ek_fast_kernel<256> (ek_sweep_fast.cu)" if on_fast else "ek_sweep_kernel<16,false,true> (ek_sweep.cu)",
+                "fast_kernel_qualified": bool(L.ek_fast_mode()), "kernel_ms": kern_ms,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"}
 
     # ---- e2e: pinned host buffers, H2D of the 4 inputs + D2H of the result inside the timed region
@@ -442,6 +469,30 @@ def main():
                "h2d_bytes_per_step": 4 * n * 4, "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_ms,
                "pipeline": f"{E2E_CHUNKS} chunks; H2D + kernels on the compute stream, read-back on a second stream",
                "pcie_gbs": (5 * n * 4) / (e2e_ms * 1e-3) / 1e9}
+        # PCIe ceiling beside it: the same bytes (4 inputs up, 1 result down) with NO kernels in between -- uploads on the
+        # compute stream, the read-back of the previous chunk on the second stream, pinned buffers, same chunking
+        try:
+            cn = n // E2E_CHUNKS
+            dbuf = [L.ek_malloc(cn * 4) for _ in range(5)]
+
+            def copies_only():
+                for c in range(E2E_CHUNKS):
+                    for k in range(4):
+                        L.ek_memcpy_to_device_async(dbuf[k], hb[k] + c * cn * 4, cn * 4)
+                    L.ek_memcpy_from_device_overlapped(hb[4] + c * cn * 4, dbuf[4], cn * 4)
+                ek.cuda_sync()
+            copies_only()
+            tc = time.time()
+            for _ in range(3):
+                copies_only()
+            ceil_ms = 1e3 * (time.time() - tc) / 3
+            for d in dbuf:
+                L.ek_free(d)
+            e2e["pcie_ceiling_ms"] = ceil_ms
+            e2e["pcie_ceiling_gbs"] = (5 * n * 4) / (ceil_ms * 1e-3) / 1e9
+            e2e["frac_of_pcie_ceiling"] = ceil_ms / e2e_ms
+        except Exception as e:
+            e2e["pcie_ceiling_error"] = repr(e)
         for p in hb:
             L.ek_host_free(p)
 
@@ -485,6 +536,23 @@ def main():
     if not args.skip_backward:
         backward = bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs)
 
+    backward_narrow = None
+    if not args.skip_backward and rank == 0 and not args.skip_extras:
+        try:        # the same tape at node width 16 384: the regime where the host walk, not HBM, limits backward()
+            backward_narrow = bench_backward(ek, L, rank, 1, None, torch, local_rank, peak_gbs, width=16384)
+        except Exception as e:
+            backward_narrow = {"error": repr(e)}
+
+    # ---- C5 (configs[4]): differentiable ray-sphere render through the C++ header API (tools/c5_bench.cpp)
+    c5 = None
+    if rank == 0 and not args.skip_extras:
+        c5 = bench_c5(peak_gbs, local_rank)
+
+    # ---- C1 (configs[0]): the reference's CPU path alone, operator form and vectorize() form at 2^20
+    c1 = None
+    if rank == 0 and not args.skip_cpu:
+        c1 = bench_c1()
+
     # ---- CPU baseline beside it (rank 0, bounded sample)
     cpu = None
     if rank == 0 and not args.skip_cpu:
@@ -508,14 +576,72 @@ def main():
             "config": {"workload": "C2: CUDAArray<float> 64M-elem fused arith+exp/sin chain, cuda_eval() (+ fused hsum, NCCL all-reduce of the scalar when N>1)",
                        "elems_per_gpu": n, "nodes": C2_NODES, "bytes_per_elem": C2_BYTES_PER_ELEM,
                        "l2": "inputs 4 x 256 MiB per step exceed the 126 MB L2 (no explicit flush needed)",
-                       "parallelism": f"element-range sharding x{world}, one rank per GPU"},
+                       "parallelism": f"element-range sharding x{world}, one rank per GPU",
+                       "collective": ("ncclAllReduce of the loss scalar by the library (C ABI ek_allreduce_scalars)" if native_nccl else
+                                      "torch.distributed all_reduce of the loss scalar on the backend's stream") if world > 1 else "none (1 GPU)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "backward": backward, "histogram": hist, "small": small, "wall_ms_per_step": wall_ms / args.steps, "loss_checksum": loss_val,
+            "backward": backward, "backward_width_16384": backward_narrow, "histogram": hist, "c5": c5, "c1_cpu": c1, "small": small, "wall_ms_per_step": wall_ms / args.steps, "loss_checksum": loss_val,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_c5(peak_gbs, local_rank):
+    """BASELINE configs[4]: 4096 x 4096 differentiable ray-sphere render, forward + backward, written against
+    enoki::DiffArray<enoki::CUDAArray<float>> (tools/c5_bench.cpp, built in the dev container against the reference's API
+    headers).  Runs as a child process on the same GPU after this process has finished its own timing; reports ms per
+    forward+backward step, the bytes the launched kernels streamed with graph simplification on / off, and those bytes
+    against the measured HBM peak.  (Parity of this render against the reference CPU tape: tests/cpp/sphere_check.cpp.)"""
+    exe = os.path.join(ROOT, "tools", "c5_bench")
+    if not os.path.exists(exe):
+        return {"error": "tools/c5_bench is not built (needs the reference headers at build time: __graft_entry__.build())"}
+    try:
+        env = dict(os.environ, LOCAL_RANK=str(local_rank))
+        r = subprocess.run([exe, "4096", "5"], capture_output=True, text=True, timeout=600, env=env)
+        if r.returncode != 0:
+            return {"error": f"c5_bench rc={r.returncode}: {r.stderr[-400:]}"}
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        for key in ("simplify_on", "simplify_off"):
+            o = d.get(key)
+            if o:
+                total = o["sweep_bytes_per_step"] + o["adjoint_bytes_per_step"]
+                o["bytes_streamed_per_step"] = total
+                o["roofline"] = {"bound": "hbm", "achieved": total / (o["ms_per_step"] * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                                 "frac": total / (o["ms_per_step"] * 1e-3) / 1e9 / peak_gbs,
+                                 "note": "bytes the launched kernels streamed (sweep loads + stores, 10 B per edge-adjoint) over the wall "
+                                         "time of one traced forward+backward step incl. host tracing; SURVEY 8d nominal: forward 201 MB"}
+        d["n_gpus"] = 1
+        return d
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def bench_c1():
+    """BASELINE configs[0]: r = a*b + sin(c) on DynamicArray<Packet<float,8>>, N = 2^20 -- the reference's own
+    CPU path (oracle/_ref), operator form and vectorize() form, one thread (Enoki's CPU arrays are single-threaded)."""
+    try:
+        lib, kind = load_ref(True)
+        if kind != "reference":
+            return {"error": "oracle/_ref is not built"}
+        out = (ctypes.c_float * 1)()
+        n = 1 << 20
+        res = {"workload": "C1: DynamicArray<Packet<float,8>> 1M-elem a*b+sin(c), AVX2+FMA -ffp-contract=fast, 1 thread, best of 50",
+               "elems": n, "nproc": os.cpu_count(), "cpu_quota": host_cores()}
+        for name in ("operator", "vectorized"):
+            f = getattr(lib, f"ref_c1_time_{name}")
+            f.restype = ctypes.c_double
+            t = f(ctypes.c_size_t(n), 50, out)
+            res[name] = {"ms": t * 1e3, "m_elems_per_s": n / t / 1e6, "m_array_ops_per_s": 3 * n / t / 1e6,
+                         "gb_per_s": 16.0 * n / t / 1e9}
+        try:
+            res["cpu_model"] = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+        except Exception:
+            pass
+        return res
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def bench_histogram(ek, L, n, peak_gbs):
@@ -551,12 +677,14 @@ def bench_histogram(ek, L, n, peak_gbs):
     ms = st.total_kernel_ms / max(int(st.sweep_launches), 1)
     total = int(b.numpy().astype(np.uint64).sum())
     return {"workload": "C3: 2^26-sample gather(31-entry table) + scatter_add(31 u32 bins, 31 f32 bins)", "kernel_ms": ms,
+            "kernel": "ek_fast_kernel<256>: per-thread private bins (integer: red.shared.add, float: LDS/FADD/STS), 9 dispatches" if int(st.fast_launches) > 0
+                      else "ek_sweep_kernel<16,false,true>: shared-memory atomics for the integer bins, private float bins",
             "m_samples_per_s": n / (ms * 1e-3) / 1e6, "in_range": total,
             "roofline": {"bound": "hbm", "achieved": 4.0 * n / (ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                          "frac": 4.0 * n / (ms * 1e-3) / 1e9 / peak_gbs, "bytes_per_sample": 4.0}}
 
 
-def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
+def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs, width=None):
     """80 levels x 128 nodes, node width 131072, 2 in-edges per non-leaf node to random
     nodes of the previous level, materialised fp32 weights U(0.5,1.5) with 1% exact zeros, loss = hsum
     over the last level.  Algorithmic traffic: weights once + adjoints written once and read once per
@@ -564,7 +692,7 @@ def bench_backward(ek, L, rank, world, dist, torch, local_rank, peak_gbs):
     from enoki_b200 import Float32, UInt32, fmadd, select
     F32 = ek.EK_FLOAT32
     L.ek_tape_set_graph_simplification(F32, 0)      # C4 is defined on materialised weights
-    Lv, K, w = C4["levels"], C4["per_level"], C4["width"]
+    Lv, K, w = C4["levels"], C4["per_level"], (width or C4["width"])
     rng = np.random.default_rng(1234 + rank)
     idx = UInt32.arange(w)
     ids = [[0] * K for _ in range(Lv)]

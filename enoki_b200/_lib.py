@@ -24,6 +24,13 @@ class ek_stats(ctypes.Structure):
 # name -> (restype, argtypes); every symbol include/enoki_b200.h declares
 SIGNATURES = {
     "ek_init": (c_int, []),
+    "ek_dist_unique_id": (c_int, [c_vp]),
+    "ek_dist_init": (c_int, [c_int, c_int, c_vp]),
+    "ek_dist_rank": (c_int, []),
+    "ek_dist_world": (c_int, []),
+    "ek_allreduce": (c_int, [c_int, c_vp, c_sz]),
+    "ek_allreduce_scalars": (c_int, [c_vp, c_sz]),
+    "ek_dist_shutdown": (None, []),
     "ek_set_fast_mode": (None, [c_int]),
     "ek_fast_mode": (c_int, []),
     "ek_shutdown": (None, []),

@@ -43,3 +43,73 @@ def allreduce_device_scalar(ptr, dtype, stream_ptr, device):
         ten = torch.as_tensor(_Dev(ptr, typestr), device=device)
         dist.all_reduce(ten)
     return ten
+
+
+_native = {"ok": False}
+
+
+def init_native(rank, world, device=None):
+    """Create the backend's OWN NCCL communicator (C ABI: ek_dist_unique_id / ek_dist_init, csrc/ek_dist.cpp) so that the
+    per-step all-reduce is one ncclAllReduce enqueued by the library on its stream -- no torch call in the step loop.
+    torch.distributed (already initialised by the launcher) only carries the 128-byte id from rank 0 to the other ranks,
+    once.  The communicator is checked with one all-reduce of the rank numbers; on any failure this returns False and
+    callers keep using allreduce_device_scalar() (torch.distributed) -- the collective path of round 1."""
+    import ctypes
+    import sys
+    import torch
+    import torch.distributed as dist
+    from . import lib
+    L = lib()
+    _native["ok"] = False
+    if world == 1:
+        _native["ok"] = L.ek_dist_init(0, 1, None) == 0
+        return _native["ok"]
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    on_gpu = dist.get_backend() == "nccl"
+
+    def all_agree(ok):
+        """every rank must take the same path: minimum of the per-rank flags (a collective every rank reaches)"""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32)
+        if on_gpu:
+            flag = flag.to(dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(int(flag.item()))
+
+    # 1. can every rank load NCCL?  (ncclCommInitRank is collective: a rank that skips it would hang the others)
+    buf = (ctypes.c_uint8 * 128)()
+    ok = L.ek_dist_unique_id(buf) == 0
+    if not ok:
+        print(f"enoki_b200.dist: rank {rank}: {L.ek_last_error().decode()}", file=sys.stderr)
+    if not all_agree(ok):
+        return False
+    # 2. rank 0's id to everybody
+    ident = torch.tensor(list(buf), dtype=torch.uint8)
+    if on_gpu:
+        ident = ident.to(dev)
+    dist.broadcast(ident, src=0)
+    raw = bytes(ident.cpu().tolist())
+    # 3. the communicator, then one all-reduce of the rank numbers as a self-check
+    ok = L.ek_dist_init(rank, world, ctypes.c_char_p(raw)) == 0
+    if not ok:
+        print(f"enoki_b200.dist: rank {rank}: {L.ek_last_error().decode()}", file=sys.stderr)
+    if not all_agree(ok):
+        return False
+    from . import Float32
+    probe = Float32.copy(np.array([float(rank + 1)], np.float32))
+    h = (ctypes.c_uint32 * 1)(probe.index)
+    ok = L.ek_allreduce_scalars(h, 1) == 0 and abs(float(probe.numpy()[0]) - world * (world + 1) / 2) < 1e-6
+    _native["ok"] = all_agree(ok)
+    return _native["ok"]
+
+
+def native_ready():
+    return _native["ok"]
+
+
+def allreduce_handles(arrays):
+    """Sum the given size-1 (or small) backend arrays over all ranks through the library's own communicator."""
+    import ctypes
+    from . import lib
+    h = (ctypes.c_uint32 * len(arrays))(*[a.index for a in arrays])
+    if lib().ek_allreduce_scalars(h, len(arrays)) != 0:
+        raise RuntimeError(lib().ek_last_error().decode())

@@ -241,6 +241,19 @@ typedef struct ek_stats {
     float    total_kernel_ms;   /* sum of device times since reset (timing mode only)     */
     uint64_t fast_launches;     /* ... sweeps that ran on the 32-bit fast kernel (ek_sweep_fast.cu) */
 } ek_stats;
+/* ------------------------------------------------------------------ multi-GPU (no counterpart in the reference)
+ * One rank (process) per GPU, element-range sharding, ONE all-reduce of the size-1 results per step (the local hsum is
+ * where the reference has it, autodiff.cpp:867-871).  NCCL is dlopen()ed on first use (EK_NCCL_LIB, else libnccl.so.2).
+ * Rank 0: ek_dist_unique_id() -> hand the EK_DIST_ID_BYTES bytes to the other ranks; all ranks: ek_dist_init(). */
+#define EK_DIST_ID_BYTES 128
+EK_API int  ek_dist_unique_id(void *out_id);                         /* ncclGetUniqueId */
+EK_API int  ek_dist_init(int rank, int world, const void *id);       /* ncclCommInitRank on the device of ek_set_device() */
+EK_API int  ek_dist_rank(void);
+EK_API int  ek_dist_world(void);
+EK_API int  ek_allreduce(ek_type type, void *data, size_t count);    /* in-place sum on the backend's stream */
+EK_API int  ek_allreduce_scalars(const uint32_t *handles, size_t n); /* evaluate + sum the given variables over all ranks */
+EK_API void ek_dist_shutdown(void);
+
 /* 32-bit fast sweep kernel (no counterpart in the reference): ek_init() enables it after the kernel qualification
    described in csrc/ek_runtime.cpp (or as EK_FAST=0/1 says); these calls read / override that decision. */
 EK_API void ek_set_fast_mode(int enable);

@@ -228,6 +228,36 @@ double ref_c2_time_vectorized(float *x0_, float *x1_, float *x2_, float *x3_, fl
     return best;
 }
 
+/* ---- C1 (BASELINE.json configs[0]): r = a*b + sin(c) on DynamicArray<Packet<float,8>>, N = 2^20,
+        a = linspace(0,1), b = linspace(1,2), c = linspace(-3,3) -- operator form (one heap pass per operator,
+        dynamic.h:275-443) and the fused vectorize() form (dynamic.h:1025-1074, tests/dynamic.cpp:192-225).
+        Returns the best pass in seconds; out[0] receives r[n/2] so that nothing is optimised away. */
+double ref_c1_time_operator(size_t n, int reps, float *out) {
+    FloatX a = linspace<FloatX>(0.f, 1.f, n), b = linspace<FloatX>(1.f, 2.f, n), c = linspace<FloatX>(-3.f, 3.f, n);
+    double best = 1e30;
+    for (int i = 0; i < reps; ++i) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        FloatX r = a * b + sin(c);
+        auto t1 = std::chrono::high_resolution_clock::now();
+        out[0] = r.coeff(n / 2);
+        best = std::min(best, std::chrono::duration<double>(t1 - t0).count());
+    }
+    return best;
+}
+double ref_c1_time_vectorized(size_t n, int reps, float *out) {
+    FloatX a = linspace<FloatX>(0.f, 1.f, n), b = linspace<FloatX>(1.f, 2.f, n), c = linspace<FloatX>(-3.f, 3.f, n);
+    FloatX r = zero<FloatX>(n);
+    double best = 1e30;
+    for (int i = 0; i < reps; ++i) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        vectorize([](auto &&r, auto &&a, auto &&b, auto &&c) { r = a * b + sin(c); }, r, a, b, c);
+        auto t1 = std::chrono::high_resolution_clock::now();
+        out[0] = r.coeff(n / 2);
+        best = std::min(best, std::chrono::duration<double>(t1 - t0).count());
+    }
+    return best;
+}
+
 /* ---- PCG32 (random.h:40-119): stream = element index, default state ---- */
 void ref_pcg32_u32(uint64_t first, size_t n, size_t draws, uint32_t *out) {
     /* out[d * n + i] = d-th draw of the generator with stream (first + i) */
