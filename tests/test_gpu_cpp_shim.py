@@ -43,18 +43,6 @@ def test_cpp_autodiff_parity(gpu):
     assert "all checks passed" in r.stdout
 
 
-@pytest.mark.parametrize("n", ["1000", "100003", "4194304"])
-def test_cpp_virtual_call_dispatch(gpu, n):
-    """SURVEY 8f row 1: ENOKI_CALL_SUPPORT dispatch through CUDAArray<T *>::partition_() -> ek_partition, compared bit
-    for bit with the same classes called on the reference CPU path (array_call.h:124-193)."""
-    binp = os.path.join(os.path.dirname(BIN), "call_check")
-    if not os.path.exists(binp):
-        pytest.skip("tests/cpp/call_check not built (needs the reference headers at build time)")
-    r = subprocess.run([binp, n], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "all checks passed" in r.stdout
-
-
 def test_cpp_integer_morton_parity(gpu):
     """North star: bit-exact integer / indexing / Morton ops.  tests/cpp/int_check.cpp runs the same templates
     (arithmetic, shifts, mulhi, div/mod, division by constants, popcnt/lzcnt/tzcnt, Morton 2-D/3-D encode + decode,

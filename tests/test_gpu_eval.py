@@ -426,42 +426,6 @@ def test_psum_compress_raw(gpu):
     assert (got == u[mask]).all()
 
 
-@pytest.mark.parametrize("n,k", [(1, 1), (31, 3), (100_003, 7), (1 << 22, 40), (50_000, 1500)])
-def test_partition(gpu, n, k):
-    """cuda_partition (horiz.cu:35-122) feeds virtual-call dispatch: groups of indices per distinct pointer, pointers
-    ascending, indices ascending inside a group (what the reference's stable radix sort + RLE produces).
-    k = 1500 exceeds the distinct-value table and takes the host fallback."""
-    ek = gpu
-    L = ek.lib()
-    rng = np.random.default_rng(n + k)
-    # k distinct 16-byte aligned "pointers" below 2^44.  (NEVER materialise the value range: the first version of this test
-    # said rng.choice(np.arange(1, 1 << 40)) -- an 8 TiB host array -- and every GPU box that ran it was lost to the host's
-    # OOM killer after ~2 minutes; that, not ek_partition, is what "hung" in rounds 1 and 2.)
-    cand = np.unique(rng.integers(1, 1 << 40, size=4 * k + 16, dtype=np.uint64))
-    assert len(cand) >= k
-    table = np.sort(rng.permutation(cand)[:k]) * np.uint64(16)
-    ptr = table[rng.integers(0, k, n)]
-    P64 = ek.UInt64.copy(ptr)
-    uniq = ctypes.c_void_p(); counts = ctypes.c_void_p(); perm = ctypes.c_void_p()
-    assert L.ek_partition(n, P64.data(), ctypes.byref(uniq), ctypes.byref(counts), ctypes.byref(perm)) == 0, L.ek_last_error()
-    cnt = np.ctypeslib.as_array(ctypes.cast(counts.value, ctypes.POINTER(ctypes.c_uint32)), shape=(1,))
-    K = int(cnt[0])
-    want_u, want_c = np.unique(ptr, return_counts=True)
-    assert K == len(want_u)
-    cnt = np.ctypeslib.as_array(ctypes.cast(counts.value, ctypes.POINTER(ctypes.c_uint32)), shape=(K + 1,)).copy()
-    un = np.ctypeslib.as_array(ctypes.cast(uniq.value, ctypes.POINTER(ctypes.c_uint64)), shape=(K,)).copy()
-    assert (un == want_u).all() and (cnt[1:] == want_c).all()
-    pp = np.ctypeslib.as_array(ctypes.cast(perm.value, ctypes.POINTER(ctypes.c_uint64)), shape=(K,)).copy()
-    order = np.argsort(ptr, kind="stable").astype(np.uint32)
-    off = 0
-    for i in range(K):
-        got = ek.UInt32.map(int(pp[i]), int(cnt[i + 1]), True).numpy()
-        assert (got == order[off:off + cnt[i + 1]]).all(), i
-        off += int(cnt[i + 1])
-    L.ek_host_free(uniq); L.ek_host_free(counts)
-    libc = ctypes.CDLL(None); libc.free.argtypes = [ctypes.c_void_p]; libc.free(perm)
-
-
 def test_histogram_full_size_properties(gpu):
     """C3 at BASELINE size (2^26 samples): gather from a 31-entry table + scatter_add into 31 uint32 / float bins.
     Size-independent properties: the integer bins equal numpy's bincount of the device-computed indices (bit-exact),
