@@ -9,6 +9,8 @@
 #include <enoki/dynamic.h>
 #include <cstdio>
 #include <cmath>
+#include <cstring>
+#include <cstdint>
 #include <vector>
 #include <string>
 #include <functional>
@@ -142,28 +144,53 @@ SCENARIO(s_descent) { TYPES            /* tests/autodiff.cpp:550-562: a few step
     std::vector<float> r; append(r, x); return r;
 }
 
-struct Case { const char *name; std::function<std::vector<float>()> cpu, gpu; float tol; };
-#define CASE(fn, tol) Case { #fn, fn<DiffArray<FloatX>>, fn<DiffArray<FloatC>>, tol }
+/* distance in units in the last place between two floats (0 for equal values incl. +-0; NaN vs NaN = 0) */
+static double ulp_dist(float a, float b) {
+    if (a == b || (std::isnan(a) && std::isnan(b))) return 0;
+    if (std::isnan(a) || std::isnan(b) || std::isinf(a) || std::isinf(b)) return 1e30;
+    int32_t ia, ib; memcpy(&ia, &a, 4); memcpy(&ib, &b, 4);
+    auto key = [](int32_t v) -> int64_t { return v < 0 ? (int64_t) 0x80000000ll - (int64_t) (uint32_t) v : (int64_t) v; };   /* monotone in the float order */
+    return std::fabs((double) (key(ia) - key(ib)));
+}
+
+/* Gates (north star: 1 ulp for fp32 arithmetic, 4 ulp for transcendentals, reductions by reassociation bound):
+     max_ulp >= 0 : every value within that many ulp of the reference CPU tape (values of magnitude below 1e-30 are
+                    compared absolutely: a gradient that is exactly 0 on one side and 1e-40 on the other is not 1e9 ulp)
+     max_ulp <  0 : the chain contains rcp / rsqrt (the CPU path is rcpps / rsqrtps + one Newton step, itself up to 3 ulp from
+                    the correctly rounded value and CPU-vendor dependent, array_avx.h:324-395), composite functions built on
+                    them (tan, sinh, tanh, atan2, asin: array_math.h), or float reductions folded in a different order
+                    (hsum, psum): only the relative bound `tol` applies -- the observed max ulp is still printed. */
+struct Case { const char *name; std::function<std::vector<float>()> cpu, gpu; float tol; double max_ulp; };
+#define CASE(fn, tol, ulp) Case { #fn, fn<DiffArray<FloatX>>, fn<DiffArray<FloatC>>, tol, ulp }
 
 int main() {
     if (ek_device_count() == 0) { fprintf(stderr, "no CUDA device\n"); return 2; }
     std::vector<Case> cases = {
-        CASE(s_arith, 2e-5f), CASE(s_trig, 2e-5f), CASE(s_select, 1e-6f), CASE(s_broadcast, 2e-5f), CASE(s_hprod, 2e-5f),
-        CASE(s_scatter_add, 1e-6f), CASE(s_scatter, 1e-6f), CASE(s_gather, 1e-6f), CASE(s_gather_fwd, 1e-6f),
-        CASE(s_scatter_fwd, 1e-6f), CASE(s_forward, 2e-5f), CASE(s_psum_reverse, 2e-5f), CASE(s_descent, 1e-5f) };
+        /* Round 2: every ulp gate is still "report only" (-1).  The scenarios build their inputs with linspace(), which the
+           reference evaluates differently on its CPU and CUDA paths (dynamic.h:923-938 vs cuda.h:655-663), so an input may
+           already differ by an ulp; the gates can only be set from the numbers this program prints on hardware, and the
+           repository had no GPU access when the ulp report was added.  The Python tests (tests/test_gpu_eval.py,
+           test_gpu_tape.py) feed identical inputs to both sides and ARE bit-exact gates. */
+        CASE(s_arith, 2e-5f, -1), CASE(s_trig, 2e-5f, -1), CASE(s_select, 1e-6f, -1), CASE(s_broadcast, 2e-5f, -1), CASE(s_hprod, 2e-5f, -1),
+        CASE(s_scatter_add, 1e-6f, -1), CASE(s_scatter, 1e-6f, -1), CASE(s_gather, 1e-6f, -1), CASE(s_gather_fwd, 1e-6f, -1),
+        CASE(s_scatter_fwd, 1e-6f, -1), CASE(s_forward, 2e-5f, -1), CASE(s_psum_reverse, 2e-5f, -1), CASE(s_descent, 1e-5f, -1) };
     int failures = 0;
     for (auto &c : cases) {
         std::vector<float> a, b;
         try { a = c.cpu(); b = c.gpu(); }
         catch (const std::exception &e) { printf("%-16s EXCEPTION %s\n", c.name, e.what()); ++failures; continue; }
         bool ok = a.size() == b.size() && !a.empty();
-        double maxd = 0;
+        double maxd = 0, maxu = 0;
         for (size_t i = 0; ok && i < a.size(); ++i) {
             double d = std::fabs((double) a[i] - b[i]) / std::max(1.0, std::fabs((double) a[i]));
             if (!(d <= c.tol)) ok = false;
             maxd = std::max(maxd, d);
+            double u = (std::fabs(a[i]) < 1e-30f && std::fabs(b[i]) < 1e-30f) ? 0.0 : ulp_dist(a[i], b[i]);
+            maxu = std::max(maxu, u);
         }
-        printf("%-16s %s  n=%zu/%zu  max rel diff %.3g\n", c.name, ok ? "ok  " : "FAIL", a.size(), b.size(), maxd);
+        if (ok && c.max_ulp >= 0 && maxu > c.max_ulp) ok = false;
+        printf("%-16s %s  n=%zu/%zu  max rel diff %.3g  max ulp %.0f (gate: %s)\n", c.name, ok ? "ok  " : "FAIL", a.size(), b.size(), maxd, maxu,
+               c.max_ulp >= 0 ? "ulp" : "relative bound only");
         if (!ok) for (size_t i = 0; i < std::min(a.size(), b.size()); ++i) printf("    [%zu] cpu % .9g  gpu % .9g\n", i, a[i], b[i]);
         if (!ok) ++failures;
     }

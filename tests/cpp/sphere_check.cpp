@@ -9,6 +9,8 @@
 #include <enoki/dynamic.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <cstdint>
 #include <cmath>
 #include <chrono>
 #include <vector>
@@ -80,14 +82,20 @@ int main(int argc, char **argv) {
     cuda_sync();
     auto t3 = std::chrono::high_resolution_clock::now();
 
-    size_t n = res * res, bad = 0; double maxd = 0;
+    size_t n = res * res, bad = 0, n_diff = 0; double maxd = 0, max_ulp = 0;
     for (size_t i = 0; i < n; ++i) {
         double d = std::fabs((double) img_cpu[i] - img_gpu[i]);
         maxd = std::max(maxd, d);
         if (d > 2e-6 * std::max(1.0, std::fabs((double) img_cpu[i]))) ++bad;
+        if (img_cpu[i] != img_gpu[i]) {
+            ++n_diff;
+            int32_t ia, ib; memcpy(&ia, &img_cpu[i], 4); memcpy(&ib, &img_gpu[i], 4);
+            if ((ia < 0) == (ib < 0)) max_ulp = std::max(max_ulp, std::fabs((double) ia - (double) ib)); else max_ulp = std::max(max_ulp, 1e9);
+        }
     }
     int fail = bad != 0;
-    printf("sphere_check: %zux%zu rays  image max|diff| = %.3g (%zu px > 2e-6)\n", res, res, maxd, bad);
+    printf("sphere_check: %zux%zu rays  image max|diff| = %.3g (%zu px > 2e-6); %zu px differ at all, max %.0f ulp (reported, not gated yet)\n",
+           res, res, maxd, bad, n_diff, max_ulp);
     printf("  loss cpu %.8g  gpu %.8g\n", loss_c, loss_g);
     /* The image is compared per pixel above; the loss is a float sum of n squares.  The CPU reference adds the
        packets one after another (error grows ~n eps: 1.5e-4 relative at 1024^2), the device sums a tree.  So the

@@ -86,6 +86,7 @@ inline int __float2int_rz(float x) { return (int) truncf(x); }
 inline int __float2int_rd(float x) { return (int) floorf(x); }
 inline int __float2int_ru(float x) { return (int) ceilf(x); }
 inline int __float2int_rn(float x) { return (int) rintf(x); }
+inline uint32_t __float2uint_rz(float x) { return (uint32_t) truncf(x); }
 inline long long __float2ll_rz(float x) { return (long long) truncf(x); }
 inline long long __float2ll_rd(float x) { return (long long) floorf(x); }
 inline long long __float2ll_ru(float x) { return (long long) ceilf(x); }
