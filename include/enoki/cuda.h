@@ -379,7 +379,7 @@ struct CUDAArray : ArrayBase<value_t<Value>, CUDAArray<Value>> {
 
     /// Virtual-call dispatch support (cuda.h:814-843): (instance pointer, indices that refer to it), pointers ascending,
     /// indices ascending; cached per array like the reference's.
-    /// Round 1: ek_partition is unverified and answers with an error unless EK_ENABLE_PARTITION=1 (see ek_scan.cu).
+    /// (ek_partition: host-side stable sort by default, device composition with EK_PARTITION_DEVICE=1, see ek_scan.cu.)
     template <typename T = Value, enable_if_t<std::is_pointer_v<T> || std::is_same_v<T, uintptr_t>> = 0>
     std::vector<std::pair<Value, CUDAArray<uint32_t>>> partition_() const {
         using Groups = std::vector<std::pair<Value, CUDAArray<uint32_t>>>;
