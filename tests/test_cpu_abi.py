@@ -257,3 +257,17 @@ def test_resize_of_a_lazy_reduction_broadcasts(ek):
     assert L.ek_var_set_size(s2.index, 500, 0) == 0 and b"resize" in L.ek_last_error()
     del s, s2, x
     gc.collect(); ek.lib().ek_debug_discard_side_effects()
+
+
+def test_qualification_battery_records_and_plans():
+    """enoki_b200/ek_qualify --dry: every program of the kernel-qualification battery (csrc/ek_qualify.cpp) is recorded
+    through the C ABI and planned in both modes (general kernels / fast kernel) on the host -- the battery itself must not be
+    what fails on the GPU box."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "enoki_b200", "ek_qualify")
+    assert os.path.exists(exe), "enoki_b200/ek_qualify is not built (make -C enoki_b200/csrc)"
+    r = subprocess.run([exe, "--dry"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "recorded and planned in both modes" in r.stderr

@@ -9,7 +9,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 3 --skip-cpu > gpurun_out/ncu_launches_$tag.log 2>&1
 # full captures
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ek_sweep -s 3 -c 1 -f -o gpurun_out/prof_sweep_$tag \
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:ek_fast|ek_sweep' -s 3 -c 1 -f -o gpurun_out/prof_sweep_$tag \
     python bench.py --steps 2 --warmup 3 --skip-backward --skip-cpu > gpurun_out/ncu_sweep_$tag.log 2>&1
 ncu -i gpurun_out/prof_sweep_$tag.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py > gpurun_out/ncu_sweep_${tag}_summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ek_adjoint -s 100 -c 1 -f -o gpurun_out/prof_adjoint_$tag \
