@@ -347,3 +347,29 @@ print("device partition ok")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, EK_PARTITION_DEVICE="1"))
     assert r.returncode == 0 and "device partition ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_two_rank_sharded_matches_single_gpu(gpu):
+    """SURVEY 8e on hardware (needs 2 GPUs, skipped otherwise): element-range sharding over two ranks + ONE all-reduce of the
+    size-1 results reproduces the single-GPU loss and scalar gradients within the reassociation bound -- through
+    torch.distributed (the round-1 transport) and through the library's own NCCL communicator (C ABI, csrc/ek_dist.cpp)."""
+    import json
+    try:
+        import torch
+        n_gpu = torch.cuda.device_count()
+    except Exception:
+        n_gpu = 0
+    if n_gpu < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29500 + (os.getpid() % 400)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "two_rank_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = next((l for l in r.stdout.splitlines() if l.startswith("TWO_RANK_RESULT ")), None)
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads(line[len("TWO_RANK_RESULT "):])
+    single = np.array(res["single"], np.float64)
+    scale = np.maximum(np.abs(single), 1.0)
+    assert (np.abs(np.array(res["torch"]) - single) <= 1e-5 * scale).all(), res
+    assert res["native"] is not None, "the native NCCL communicator could not be created (see the worker's stderr): " + r.stderr[-1500:]
+    assert (np.abs(np.array(res["native"]) - single) <= 1e-5 * scale).all(), res
