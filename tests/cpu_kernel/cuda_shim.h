@@ -100,6 +100,10 @@ inline long long __double2ll_rd(double x) { return (long long) floor(x); }
 inline long long __double2ll_ru(double x) { return (long long) ceil(x); }
 inline long long __double2ll_rn(double x) { return (long long) rint(x); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned) v); }
+inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
+inline int __mulhi(int a, int b) { return (int) (((long long) a * (long long) b) >> 32); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned) (((unsigned long long) a * b) >> 32); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
 using std::max;
 using std::min;

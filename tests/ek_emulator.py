@@ -440,6 +440,29 @@ class Emulator:
                 elif name == "ABS_I32": R = np.where(R.view(np.int32) < 0, np.uint32(0) - R, R)
                 elif name == "MULHI_U32": R = ((R.astype(np.uint64) * B.astype(np.uint64)) >> np.uint64(32)).astype(np.uint32)
                 elif name == "MULHI_I32": R = ((R.view(np.int32).astype(np.int64) * B.view(np.int32).astype(np.int64)) >> np.int64(32)).astype(np.int32).view(np.uint32)
+                elif name in ("DIV_U32", "DIVR_U32", "MOD_U32", "MODR_U32"):
+                    a, b = (R, B) if not name.startswith(("DIVR", "MODR")) else (B, R)
+                    bz = b == 0
+                    bs = np.where(bz, np.uint32(1), b)
+                    R = np.where(bz, np.uint32(0xffffffff), a // bs) if name.startswith("DIV") else np.where(bz, a, a % bs)
+                elif name in ("DIV_I32", "DIVR_I32", "MOD_I32", "MODR_I32"):
+                    a, b = (R, B) if not name.startswith(("DIVR", "MODR")) else (B, R)
+                    a = a.view(np.int32).astype(np.int64); b = b.view(np.int32).astype(np.int64)
+                    bz = b == 0
+                    bs = np.where(bz, 1, b)
+                    q = np.sign(a) * np.sign(bs) * (np.abs(a) // np.abs(bs))          # C truncation
+                    if name.startswith("DIV"):
+                        R = np.where(bz, 0, q).astype(np.int64).astype(np.int32).view(np.uint32)   # (INT_MIN / -1 wraps)
+                        R = np.where((b == -1), (np.uint32(0) - a.astype(np.int32).view(np.uint32)), R)
+                    else:
+                        R = np.where(bz | (b == -1), 0, a - q * bs).astype(np.int32).view(np.uint32)
+                elif name == "POPC_32": R = np.array([bin(int(v)).count("1") for v in R], np.uint32) if len(R) < 200000 else (_ for _ in ()).throw(Unsupported("popc of a large array"))
+                elif name == "CLZ_32": R = np.array([32 - int(v).bit_length() for v in R], np.uint32) if len(R) < 200000 else (_ for _ in ()).throw(Unsupported("clz of a large array"))
+                elif name == "CTZ_32": R = np.array([(int(v) & -int(v)).bit_length() - 1 if v else 32 for v in R], np.uint32) if len(R) < 200000 else (_ for _ in ()).throw(Unsupported("ctz of a large array"))
+                elif name == "SEXT8": R = R.astype(np.uint8).view(np.int8).astype(np.int32).view(np.uint32)
+                elif name == "SEXT16": R = R.astype(np.uint16).view(np.int16).astype(np.int32).view(np.uint32)
+                elif name == "ZEXT8": R = R & np.uint32(0xff)
+                elif name == "ZEXT16": R = R & np.uint32(0xffff)
                 elif name in ("LD_U8", "LD_S8"):
                     v = staged[cb & 0x3fff]
                     R = v.astype(np.uint32) if name == "LD_U8" else v.view(np.int8).astype(np.int32).view(np.uint32)
