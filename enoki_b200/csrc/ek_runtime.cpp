@@ -85,7 +85,7 @@ int ek_set_device(int ordinal) {
    ek_init() on a machine runs `ek_qualify` (enoki_b200/ek_qualify, built from csrc/ek_qualify.cpp) in a CHILD PROCESS.
    The child evaluates a battery of programs twice -- through the general sweep kernels that passed the round-1 GPU
    test-suite, and through the fast kernel -- and compares the results bit for bit.  Only when every comparison agrees
-   (exit status 0, within 240 s) is the fast kernel used; a wrong result, a CUDA error, a watchdog trap or a crash of the
+   (exit status 0, within 150 s) is the fast kernel used; a wrong result, a CUDA error, a watchdog trap or a crash of the
    child all leave this process on the general kernels, with one line on stderr.  The verdict is remembered in a stamp
    file keyed on the library file and the GPU name, so the battery runs once per machine, not once per process.
    EK_FAST=0 / EK_FAST=1 skip the qualification and force the answer (the child itself runs with EK_FAST=0 and switches
@@ -133,7 +133,7 @@ static int decide_fast_mode(const char *gpu_name) {
         fprintf(stderr, "enoki_b200: could not start %s -- the fast sweep kernel stays off\n", helper.c_str());
     } else {
         int status = 0; bool done = false;
-        for (int waited_ms = 0; waited_ms < 240000; waited_ms += 50) {
+        for (int waited_ms = 0; waited_ms < 150000; waited_ms += 50) {
             pid_t r = waitpid(pid, &status, WNOHANG);
             if (r == pid) { done = true; break; }
             if (r < 0) break;
