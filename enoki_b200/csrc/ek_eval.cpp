@@ -1370,7 +1370,11 @@ bool choose_config(const EkContext &ctx, const Assembled &a, size_t n, Config &c
         }
     }
     if (fast_ok) {
+        /* testing aid: EK_FAST_T=128 / 256 restricts the fast kernel to one block size (tests/test_cpu_fast_kernel.py runs
+           the host-compiled kernel on both instantiations) */
+        static const int only_T = getenv("EK_FAST_T") ? atoi(getenv("EK_FAST_T")) : 0;
         for (const Cand &c : fast_cands) {
+            if (only_T && (int) c.T != only_T) continue;
             cfg.fast = true;
             cfg.V = c.V; cfg.T = c.T; cfg.stages = 1; cfg.ctas_per_sm = c.want_ctas;
             size_t need = smem_layout(a, cfg, n_uni);

@@ -138,3 +138,17 @@ def test_directed_programs_numpy_vs_host_compiled_kernel(ek, oracle, P, n):
     r_min = hmin(y0 * y1); r_max = hmax(E.sin(y1)); r_sum = hsum(y0 * y0)
     _differential(ek, oracle, table, {"hmin": r_min, "hmax": r_max, "sum": r_sum}, float_tol=("sum",))
     gc.collect()
+
+
+def test_block_size_128_instantiation():
+    """The same cases once more with the fast kernel restricted to its 128-thread instantiation (EK_FAST_T=128 is read once
+    per process, hence the child process): operand offsets, group strides and the reduction epilogue for T = 128."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, EK_FAST_T="128")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_cpu_fast_kernel.py"), "-q", "-x",
+                        "-k", "not block_size_128", "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=1200, env=env, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
