@@ -250,6 +250,18 @@ void directed(size_t n) {
         keep("int.floor2int", op1(I, EK_OP_FLOOR2INT, x1)); keep("int.ceil2int", op1(I, EK_OP_CEIL2INT, x1));
         keep("int.tofloat", op2(F, EK_OP_ADD, op1(F, EK_OP_CVT, s), op1(F, EK_OP_CVT, h)));
         keep("int.lt", op2(B, EK_OP_LT, s, litu(0u, I)));
+        /* the remaining 32-bit operations of the fast kernel's set: integer multiply-add, signed / unsigned min, shifts by
+           an array, every comparison, NOT, float rounding modes */
+        H u2 = op2(U, EK_OP_AND, h, litu(31u));
+        keep("int.mad", op3(U, EK_OP_FMA, h, u2, i));
+        keep("int.minmax", op2(I, EK_OP_MIN, s, op2(I, EK_OP_SUB, litu(100u, I), s)));
+        keep("int.shifts", op2(U, EK_OP_XOR, op2(U, EK_OP_SHL, h, u2), op2(I, EK_OP_SHR, s, op2(I, EK_OP_AND, s, litu(7u, I)))));
+        keep("int.not", op1(U, EK_OP_NOT, h));
+        H cmp = op2(B, EK_OP_OR, op2(B, EK_OP_OR, op2(B, EK_OP_NE, h, i), op2(B, EK_OP_GE, s, litu(5u, I))),
+                    op2(B, EK_OP_AND, op2(B, EK_OP_LE, x0, x1), op2(B, EK_OP_NE, x2, x3)));
+        keep("cmp.mix", op2(B, EK_OP_XOR, cmp, op2(B, EK_OP_GT, h, litu(0x80000000u))));
+        keep("f32.round", op2(F, EK_OP_ADD, op1(F, EK_OP_ROUND, op2(F, EK_OP_MUL, x0, litf(3.3f))), op1(F, EK_OP_TRUNC, op2(F, EK_OP_MUL, x1, litf(2.7f)))));
+        keep("f32.eq", op3(F, EK_OP_SELECT, op2(B, EK_OP_EQ, op1(F, EK_OP_FLOOR, x0), op1(F, EK_OP_FLOOR, x1)), x2, x3));
     }
     {   /* reductions: min / max / prod, integer sum, a reduction reused by a wide consumer (second phase) */
         keep("red.hmin", op1(F, EK_OP_HMIN, op2(F, EK_OP_MUL, x0, x1)));
