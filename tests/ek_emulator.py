@@ -419,6 +419,8 @@ class Emulator:
                 elif name == "ABS_F32": R = R & np.uint32(0x7fffffff)
                 elif name == "NEG_F32": R = R ^ np.uint32(0x80000000)
                 elif name == "SQRT_F32": R = self._u(np.sqrt(f(R)))
+                elif name == "RCP_F32": R = self._u(np.float32(1.0) / f(R))                      # correctly rounded 1/x
+                elif name == "RSQRT_F32": R = self._u(np.float32(1.0) / np.sqrt(f(R)))
                 elif name == "EXP_F32": R = self._unary(2, R)
                 elif name == "LOG_F32": R = self._unary(3, R)
                 elif name == "SIN_F32": R = self._unary(0, R)

@@ -140,6 +140,68 @@ def test_directed_programs_numpy_vs_host_compiled_kernel(ek, oracle, P, n):
     gc.collect()
 
 
+@pytest.mark.parametrize("n", [4097, 33_333])
+def test_remaining_operations_numpy_vs_host_compiled_kernel(ek, oracle, P, n):
+    """Every operation of the fast kernel's set that the other cases do not reach: rounding modes, rcp / rsqrt / log / cos,
+    division, the tape's zero-guarded multiply-adds, integer multiply-add, signed min / max / shifts by an array, NOT, all
+    comparison flavours with array and literal operands, product / count reductions, and -- with ten input arrays -- the
+    direct global loads that take over when the inputs exceed the TMA staging budget."""
+    import gc
+    from enoki_b200 import Float32, UInt32, Int32, fmadd, select, hsum, hprod
+    import enoki_b200 as E
+    gc.collect(); ek.lib().ek_debug_discard_side_effects(); gc.collect()
+    rng = np.random.default_rng(77 + n)
+    table = {}
+    F = base._Factory(Float32, table, 0x7f0000000000); U = base._Factory(UInt32, table, 0x7a0000000000)
+    xs = [F.copy(rng.uniform(-4, 4, n).astype(np.float32)) for _ in range(4)]
+    x0, x1, x2, x3 = xs
+    us = [U.copy(rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)) for _ in range(2)]
+    u0, u1 = us
+
+    a = E.round_(x0 * 3.3) + E.trunc(x1 * 2.7) + E.ceil(x2) - E.floor(x3)
+    b = (E.rcp(x0) + E.rsqrt(abs(x1) + 0.5) + E.log(abs(x2) + 1e-3) * E.cos(x3)) / x1      # (numerator first: DIV, not the reversed form)
+    c = E.mul_nz(E.floor(x2) * 0.5, x3)
+    _differential(ek, oracle, table, {"round": a, "rcp_log_cos_div": b, "nz": c})
+    del a, b, c
+
+    s = Int32(x0 * 1000.0); t = Int32(x1 * 1000.0)
+    sh = U.copy(rng.integers(0, 32, n).astype(np.uint32)); sh7 = base._Factory(Int32, table, 0x7c0000000000).copy(rng.integers(0, 8, n).astype(np.int32))
+    d = fmadd(u0, sh, u1)                                   # integer multiply-add
+    e_ = E.min_(Int32(100) - t, s) + E.max_(s * Int32(3), t)
+    g = ((u0 ^ u1) << sh) ^ UInt32((s * Int32(5)) >> sh7)
+    h = ~u1
+    _differential(ek, oracle, table, {"mad": d, "minmax": e_, "shifts": g, "not": h})
+    del d, e_, g, h
+
+    m = (u0.neq_(u1) | (s >= Int32(5))) ^ ((x0 <= x1) & x2.neq_(x3)) ^ (u0 > UInt32(0x80000000)) ^ (s <= t) ^ u0.eq_(UInt32(7)) ^ (x2 >= x3)
+    sel = select(E.floor(x0).eq_(E.floor(x1)), x2, x3)
+    _differential(ek, oracle, table, {"cmp": m, "sel": sel})
+    del m, sel, s, t, sh, sh7
+
+    y = F.copy(rng.uniform(0.999, 1.001, n).astype(np.float32))
+    mk = x0 > 0.5
+    prod = hprod(y); cnt = E._reduce("COUNT", mk, UInt32); tot = hsum(UInt32(u0 >> UInt32(12)))
+    # (the numpy interpreter folds the product in float64, the kernel in a float32 tree: ~sqrt(n) eps apart)
+    prog = ek.debug_program()
+    _differential(ek, oracle, table, {"count": cnt, "usum": tot})
+    from ek_emulator import Emulator
+    nat = FastKernelEmulator(oracle, {k: np.array(v, copy=True) for k, v in table.items()}, base._Factory.addresses)
+    nat.run(prog)
+    want = float(np.prod(table[y.index].astype(np.float64)))
+    assert abs(float(nat.vars[prod.index][0]) - want) <= 1e-3 * abs(want)
+    del prod, cnt, tot, mk, y
+
+    # ten wide inputs in one expression: beyond the staging budget (8 slot units) -> FOP_LDG_32
+    many = [F.copy(rng.uniform(-1, 1, n).astype(np.float32)) for _ in range(10)]
+    acc = many[0]
+    for k in range(1, 10):
+        acc = fmadd(acc, many[k], many[(k * 3) % 10]) if k % 2 else acc * many[k] + x0
+    prog = ek.debug_program()
+    assert any("LDG_32" in [prog["fops"][t[0]] for t in sw["fast"]["body"]] for sw in prog["sweeps"] if "fast" in sw), "no direct global load in the lowered program"
+    _differential(ek, oracle, table, {"ldg": acc})
+    gc.collect()
+
+
 def test_block_size_128_instantiation():
     """The same cases once more with the fast kernel restricted to its 128-thread instantiation (EK_FAST_T=128 is read once
     per process, hence the child process): operand offsets, group strides and the reduction epilogue for T = 128."""
