@@ -423,7 +423,7 @@ def main():
                 "none: no ncu capture of ek_fast_kernel exists (the repository had no GPU access after the kernel was written)",
                 "algorithmic_bytes": C2_BYTES_PER_ELEM * n,
                 "kernel": "ek_fast_kernel<256> (ek_sweep_fast.cu)" if on_fast else "ek_sweep_kernel<16,false,true> (ek_sweep.cu)",
-                "fast_kernel_qualified": bool(L.ek_fast_mode()), "kernel_ms": kern_ms,
+                "fast_kernel_qualified": bool(L.ek_fast_mode()), "qualification_timing": _qualification_timing(), "kernel_ms": kern_ms,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"}
 
     # ---- e2e: pinned host buffers, H2D of the 4 inputs + D2H of the result inside the timed region
@@ -586,6 +586,15 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _qualification_timing():
+    """What enoki_b200/ek_qualify measured when ek_init() qualified the fast kernel on this machine (general vs fast kernel,
+    C2 and C3 at 2^24 elements, device time of the sweep launch); None when the qualification was skipped or failed earlier."""
+    try:
+        return json.load(open(os.path.join(ROOT, "enoki_b200", ".ek_fast_timing.json")))
+    except Exception:
+        return None
 
 
 def bench_c5(peak_gbs, local_rank):

@@ -121,7 +121,8 @@ static int decide_fast_mode(const char *gpu_name) {
     }
     /* run the battery in a child process (this process may already hold CUDA state: no fork-without-exec) */
     pid_t pid = 0;
-    char *argv[] = { const_cast<char *>(helper.c_str()), nullptr };
+    const std::string timing_file = dir + "/.ek_fast_timing.json";
+    char *argv[] = { const_cast<char *>(helper.c_str()), const_cast<char *>(timing_file.c_str()), nullptr };
     std::vector<std::string> envs;
     for (char **e = environ; e && *e; ++e) if (strncmp(*e, "EK_FAST=", 8) != 0) envs.push_back(*e);
     envs.push_back("EK_FAST=0");
@@ -143,7 +144,8 @@ static int decide_fast_mode(const char *gpu_name) {
         verdict = (done && WIFEXITED(status) && WEXITSTATUS(status) == 0) ? 1 : 0;
         if (!verdict)
             fprintf(stderr, "enoki_b200: the fast sweep kernel did NOT qualify on this machine (%s) -- general kernels are used\n",
-                    !done ? "timeout" : WIFSIGNALED(status) ? "child crashed" : "results differ / CUDA error, see above");
+                    !done ? "timeout" : WIFSIGNALED(status) ? "child crashed" :
+                    (WIFEXITED(status) && WEXITSTATUS(status) == 4) ? "correct, but not faster than the general kernel here" : "results differ / CUDA error, see above");
     }
     for (const std::string &sp : stamps) {
         const std::string tmp = sp + "." + std::to_string((long) getpid());
