@@ -12,11 +12,16 @@ plus a fused hsum of the output whose scalar is all-reduced over NCCL when N>1 (
 cross-GPU value).  Metric: M array-ops/s (DAG nodes x elements / s, jit.cu:1219-1222).
 
 The JSON line also carries
-  roofline      -- the sweep kernel's algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  roofline      -- the sweep kernel's algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json; names the kernel
+                   that ran (fast or general: ek_init()'s kernel qualification decides) and what the qualification timed
   backward      -- the C4 tape (10 240 nodes / 20 224 edges, node width 131 072): M edge-adjoints/s
-  e2e           -- same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timing)
+  e2e           -- same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timing), with the PCIe
+                   ceiling of the same copies beside it
   cpu_baseline  -- the reference's own CPU path (oracle/_ref) timed on this box's host cores
   histogram     -- C3 (configs[2]): 2^26-sample gather + scatter_add histogram, kernel time
+  c5            -- configs[4]: 4096^2 differentiable ray-sphere render, forward + backward (tools/c5_bench, C++ header API)
+  c1_cpu        -- configs[0]: the reference's CPU path alone, a*b+sin(c) at 2^20, operator form and vectorize() form
+  backward_width_16384 -- the C4 tape at node width 16 384 (host-limited regime)
   small         -- the C2 expression on 2^20 elements (launch-latency regime)
   clocks        -- nvidia-smi SM clock / throttle reasons sampled inside the timed window
 `--impl reference` times the reference CPU path alone (rank 0 only).
