@@ -69,7 +69,7 @@ class ClockSampler:
         timed region and not only after it."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)],
+                                          "-lms", "25", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -98,8 +98,14 @@ class ClockSampler:
         self.thread.join(timeout=2)
         lines = list(self.lines)
         n_all = len(lines)
+        window_note = "timed region"
         if self.window[0] is not None and self.window[1] is not None:
             inside = [l for l, t in zip(lines, self.t_lines) if self.window[0] <= t <= self.window[1] + 0.1]
+            if len(inside) < 3:
+                # a short timed region (a few ms at --steps 20) holds less than three 25 ms samples: widen by half a second on
+                # both sides -- the warm-up steps before and the kernel-timing pass after it keep the GPU under the same load
+                inside = [l for l, t in zip(lines, self.t_lines) if self.window[0] - 0.5 <= t <= self.window[1] + 0.5]
+                window_note = "timed region +- 0.5 s (warm-up / kernel-timing pass, same load)"
             if inside:
                 lines = inside
         out = "".join(lines)
@@ -126,7 +132,7 @@ class ClockSampler:
                 pass
         busy = [v for v in sm if smax and v >= 0.5 * smax] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm), "samples_whole_run": n_all}
+                "samples": len(sm), "samples_whole_run": n_all, "window": window_note}
 
 
 # --------------------------------------------------------------------------- reference CPU arm
